@@ -1,0 +1,193 @@
+/*
+ * libdnmf — C-ABI of the B200-native pyDNMFk update loop.
+ *
+ * The reference (lanl/pyDNMFk) is pure Python: it has no FFI layer, its
+ * "operator API" for the hot path is the set of numpy expressions inside
+ * pyDNMFk/dist_nmf.py and pyDNMFk/pyDNMF.py.  Each entry point below replaces
+ * one of those expressions (cited as file:line, paths relative to the
+ * reference root) and is what a maintainer would bind with ctypes from those
+ * exact lines.
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, >0 = cudaError_t, <0 = argument error
+ *     (DNMF_E_*); dnmf_last_error() gives the thread-local message.
+ *   - all matrix pointers are DEVICE pointers to C-contiguous row-major data
+ *     with an explicit leading dimension (elements, not bytes).
+ *   - dtype: DNMF_F32 / DNMF_F64 (the reference's --precision float32/float64).
+ *   - math_mode: DNMF_MATH_ACCURATE = fp32-accurate results (FFMA, or 3xTF32
+ *     split on the tcgen05 path); DNMF_MATH_TF32 = single-pass TF32.
+ *   - stream: a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - the library never allocates persistent device memory; scratch space is
+ *     passed in (`ws`, `ws_bytes`; size from dnmf_workspace_bytes()).
+ *   - all reductions are two-stage with a fixed order: results are
+ *     run-to-run deterministic.
+ */
+#ifndef DNMF_H_
+#define DNMF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNMF_F32 0
+#define DNMF_F64 1
+
+#define DNMF_MATH_ACCURATE 0
+#define DNMF_MATH_TF32 1
+
+#define DNMF_E_ARG (-1)       /* bad argument (null pointer, negative size, bad dtype) */
+#define DNMF_E_UNSUPPORTED (-2) /* k > DNMF_MAX_K or unsupported combination */
+#define DNMF_E_WORKSPACE (-3) /* workspace too small */
+#define DNMF_E_NOGPU (-4)     /* no sm_100 device */
+
+#define DNMF_MAX_K 64
+
+/* op ids for dnmf_workspace_bytes */
+#define DNMF_OP_AH 0
+#define DNMF_OP_WTA 1
+#define DNMF_OP_KL_UHT 2
+#define DNMF_OP_KL_WTU 3
+#define DNMF_OP_GRAM 4
+#define DNMF_OP_RESIDUAL 5
+#define DNMF_OP_SUMS 6
+#define DNMF_OP_NNZ 7
+
+const char* dnmf_version(void);
+const char* dnmf_last_error(void);
+/* which code path the last dnmf_ah/dnmf_wta/dnmf_kl_* call on this thread took:
+ * 0 = generic CUDA-core kernel, 1 = tcgen05 (TMA + UMMA + TMEM) kernel */
+int dnmf_last_path(void);
+/* number of kernels launched by this library on this thread since the last reset */
+int64_t dnmf_launch_count(int reset);
+int dnmf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* 0 = auto (tcgen05 when eligible), 1 = force generic kernels */
+int dnmf_set_force_generic(int on);
+
+int64_t dnmf_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype);
+
+/* ---- A-streaming contractions ------------------------------------------------
+ * dnmf_ah:  V[m x k] = A[m x n] * H[k x n]^T
+ *   replaces np.matmul(A_ij, H_j.T): dist_nmf.py:198 (2-D AH_glob), :705 via :730/:887/:967/:1023 (1-D global_mm)
+ * dnmf_wta: Y[k x n] = W[m x k]^T * A[m x n]      (transposed_out: writes Y^T [n x k], the
+ *   Reduce_scatter layout of dist_nmf.py:167-169)
+ *   replaces np.matmul(W_i.T, A_ij): dist_nmf.py:166, :705 via :749/:909/:1019
+ */
+int dnmf_ah(const void* A, int64_t lda, const void* H, int64_t ldh, void* V, int64_t ldv,
+            int64_t m, int64_t n, int64_t k, int dtype, int math_mode,
+            void* ws, int64_t ws_bytes, void* stream);
+int dnmf_wta(const void* A, int64_t lda, const void* W, int64_t ldw, void* Y, int64_t ldy,
+             int64_t m, int64_t n, int64_t k, int transposed_out, int dtype, int math_mode,
+             void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- fused KL contractions (W H is never materialised) ----------------------
+ * dnmf_kl_uht: V[m x k] = (A / (W H + eps)) * H^T     dist_nmf.py:338-339 (UHT_glob), :806,:810 (glob_UX axis=0)
+ * dnmf_kl_wtu: Y[k x n] = W^T * (A / (W H + eps))     dist_nmf.py:312-313 (WTU_glob), :806,:808 (glob_UX axis=1)
+ */
+int dnmf_kl_uht(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh,
+                void* V, int64_t ldv, int64_t m, int64_t n, int64_t k, double eps,
+                int dtype, int math_mode, void* ws, int64_t ws_bytes, void* stream);
+int dnmf_kl_wtu(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh,
+                void* Y, int64_t ldy, int64_t m, int64_t n, int64_t k, double eps, int transposed_out,
+                int dtype, int math_mode, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- k x k Gram -----------------------------------------------------------------
+ * trans = 0: X is [rows x k], G = X^T X    (W^T W: dist_nmf.py:113 via :222, :679 via :748)
+ * trans = 1: X is [k x rows], G = X X^T    (H H^T: dist_nmf.py:113 via :242, :679 via :729)
+ */
+int dnmf_gram(const void* X, int64_t ldx, int64_t rows, int64_t k, int trans, void* G,
+              int dtype, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- multiplicative updates -------------------------------------------------------
+ * dnmf_mu_update_w: W *= V / (W G + eps)            dist_nmf.py:244-245, :731-732
+ * dnmf_mu_update_h: H *= Y / (H^T G + eps)^T        dist_nmf.py:224-225, :750-751
+ *   Y element (kk, c) is read at Y[kk*y_stride_k + c*y_stride_c]  (so a Y^T shard can be used in place)
+ * dnmf_kl_update_w: W *= V / (x[j] + eps)           dist_nmf.py:366,369, :828,830  (x = row sums of H)
+ * dnmf_kl_update_h: H *= Y / (x[kk] + eps)          dist_nmf.py:386,389, :847,849  (x = column sums of W)
+ * clamp != 0 fuses the every-10th-iteration np.maximum(., eps) of pyDNMF.py:155-157,170-172 (H side only:
+ *   the reference clamps W after the H half-step has consumed the un-clamped W).
+ */
+int dnmf_mu_update_w(void* W, int64_t ldw, const void* V, int64_t ldv, const void* G,
+                     int64_t m, int64_t k, double eps, int dtype, void* stream);
+int dnmf_mu_update_h(void* H, int64_t ldh, const void* Y, int64_t y_stride_k, int64_t y_stride_c,
+                     const void* G, int64_t k, int64_t n, double eps, int clamp, int dtype, void* stream);
+int dnmf_kl_update_w(void* W, int64_t ldw, const void* V, int64_t ldv, const void* x,
+                     int64_t m, int64_t k, double eps, int dtype, void* stream);
+int dnmf_kl_update_h(void* H, int64_t ldh, const void* Y, int64_t y_stride_k, int64_t y_stride_c,
+                     const void* x, int64_t k, int64_t n, double eps, int clamp, int dtype, void* stream);
+
+/* X = max(X, lo) over a [rows x cols] matrix            pyDNMF.py:155-157,170-172 */
+int dnmf_clamp_min(void* X, int64_t ldx, int64_t rows, int64_t cols, double lo, int dtype, void* stream);
+
+/* ---- small reductions ---------------------------------------------------------------
+ * dnmf_colsum: out[j] = sum_i X[i][j]   (W.sum(axis=0): dist_nmf.py:347,:793; pyDNMF.py:187; dist_nmf.py:539,:1006)
+ * dnmf_rowsum: out[i] = sum_j X[i][j]   (H.sum(axis=1): dist_nmf.py:347,:793)
+ * dnmf_sqnorm: out[0] = sum X^2 as float64 (np.linalg.norm(X)**2: dist_nmf.py:477-478,:942-943; utils.py:388)
+ */
+int dnmf_colsum(const void* X, int64_t ldx, int64_t rows, int64_t cols, void* out,
+                int dtype, void* ws, int64_t ws_bytes, void* stream);
+int dnmf_rowsum(const void* X, int64_t ldx, int64_t rows, int64_t cols, void* out,
+                int dtype, void* ws, int64_t ws_bytes, void* stream);
+int dnmf_sqnorm(const void* X, int64_t ldx, int64_t rows, int64_t cols, double* out,
+                int dtype, void* ws, int64_t ws_bytes, void* stream);
+
+/* W /= (s + eps) ; H *= s^T                          pyDNMF.py:192-193 */
+int dnmf_normalize(void* W, int64_t ldw, int64_t m, void* H, int64_t ldh, int64_t n, int64_t k,
+                   const void* s, double eps, int dtype, void* stream);
+
+/* out[0] = ||A - W H||_F^2, out[1] = ||A||_F^2 (float64), one pass over A, no m x n temporary
+ *   replaces pyDNMF.py:208-209,215 and dist_nmf.py:556,:1024 */
+int dnmf_residual_sqnorm(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh,
+                         int64_t m, int64_t n, int64_t k, double* out, int dtype,
+                         void* ws, int64_t ws_bytes, void* stream);
+/* per-column ||A[:,q] - (W H)[:,q]||^2 and ||A[:,q]||^2 (float64 [n] each)   pyDNMF.py:231-233 */
+int dnmf_column_err(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh,
+                    int64_t m, int64_t n, int64_t k, double* num, double* den, int dtype, void* stream);
+
+/* ---- HALS column sweeps ------------------------------------------------------------
+ * dnmf_hals_w_col: t = W[:,kk]*G[kk,kk] + V[:,kk] - W G[:,kk]; W[:,kk] = max(t, eps); sq[0] = sum W[:,kk]^2 (float64)
+ *                                                     dist_nmf.py:428-429, :889-890 ; utils.py:388
+ * dnmf_scale_col:  W[:,kk] *= 1/ss  (as a division)   dist_nmf.py:431-432, :892-893
+ * dnmf_hals_h:     for kk: H[kk,:] = max(H[kk,:] + Y[kk,:] - G[kk,:] H, eps)   dist_nmf.py:450-452, :911-913
+ */
+int dnmf_hals_w_col(void* W, int64_t ldw, const void* V, int64_t ldv, const void* G, int64_t m, int64_t k,
+                    int64_t kk, double eps, double* sq, int dtype, void* ws, int64_t ws_bytes, void* stream);
+int dnmf_div_col(void* W, int64_t ldw, int64_t m, int64_t kk, const double* ss_sq, int dtype, void* stream);
+int dnmf_hals_h(void* H, int64_t ldh, const void* Y, int64_t y_stride_k, int64_t y_stride_c, const void* G,
+                int64_t k, int64_t n, double eps, int dtype, void* stream);
+
+/* ---- BCD building blocks -----------------------------------------------------------
+ * dnmf_bcd_pg_w: W = max(0, Wm - (Wm G - V) / L)      dist_nmf.py:535-537, :1002-1004
+ * dnmf_bcd_pg_h: H = max(0, Hm - (G Hm - Y) / L)      dist_nmf.py:549-552, :1018-1021
+ * dnmf_div_cols: W[:,j] /= s[j]                        dist_nmf.py:542, :1011
+ * dnmf_axpby:    out = a*x + b*y  (extrapolation Wm = W + ww (W - W_old), scaling)  dist_nmf.py:574-575, :1042-1043, :493-494
+ */
+int dnmf_bcd_pg_w(void* W, int64_t ldw, const void* Wm, int64_t ldwm, const void* V, int64_t ldv, const void* G,
+                  int64_t m, int64_t k, double L, int dtype, void* stream);
+int dnmf_bcd_pg_h(void* H, int64_t ldh, const void* Hm, int64_t ldhm, const void* Y, int64_t y_stride_k,
+                  int64_t y_stride_c, const void* G, int64_t k, int64_t n, double L, int dtype, void* stream);
+int dnmf_div_cols(void* W, int64_t ldw, int64_t m, int64_t k, const void* s, int dtype, void* stream);
+int dnmf_axpby(void* out, const void* x, const void* y, double a, double b, int64_t count, int dtype, void* stream);
+
+/* ---- shard ops: zero row/column pruning and perturbation ---------------------------
+ * dnmf_nnz_counts: row_nnz[i] = #(A[i,:] != 0), col_nnz[j] = #(A[:,j] != 0)  (int64)   utils.py:119-120
+ * dnmf_compact:    out = A[np.ix_(rowmask, colmask)] given the kept indices             utils.py:155
+ * dnmf_scatter_rows / dnmf_scatter_cols: float64 zero-filled un-prune                   utils.py:194-199
+ * dnmf_perturb_uniform: X = A * (1 + nv + 2 nv u)  with u supplied (host RNG order kept) pyDNMFk.py:42-44
+ */
+int dnmf_nnz_counts(const void* A, int64_t lda, int64_t m, int64_t n, int64_t* row_nnz, int64_t* col_nnz,
+                    int dtype, void* stream);
+int dnmf_compact(const void* A, int64_t lda, const int64_t* row_idx, int64_t mr, const int64_t* col_idx, int64_t nc,
+                 void* out, int64_t ldo, int dtype, void* stream);
+int dnmf_scatter_rows(const void* X, int64_t ldx, const int64_t* row_idx, int64_t mr, int64_t cols,
+                      double* out, int64_t ldo, int dtype, void* stream);
+int dnmf_scatter_cols(const void* X, int64_t ldx, const int64_t* col_idx, int64_t nc, int64_t rows,
+                      double* out, int64_t ldo, int dtype, void* stream);
+int dnmf_perturb_uniform(const void* A, const void* U, void* X, int64_t count, double noise_var,
+                         int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNMF_H_ */

@@ -1,0 +1,23 @@
+// Interface between the C-ABI dispatch (dnmf_api.cu) and the tcgen05 / TMA / TMEM path (dnmf_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dnmf {
+
+// true when the tcgen05 path handles this call: fp32, k in {16, 32, 64}, 16-byte aligned shard with
+// lda % 4 == 0, shard large enough to fill the machine, sm_100 device, and not forced off.
+bool tc_eligible(int op, const void* A, int64_t lda, int64_t m, int64_t n, int64_t k, int dtype);
+int64_t tc_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype);
+
+int tc_ah(const float* A, int64_t lda, const float* H, int64_t ldh, float* V, int64_t ldv, int64_t m, int64_t n,
+          int k, int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st);
+int tc_wta(const float* A, int64_t lda, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t m, int64_t n,
+           int k, int transposed_out, int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st);
+int tc_kl_uht(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* V,
+              int64_t ldv, int64_t m, int64_t n, int k, float eps, int math_mode, void* ws, int64_t ws_bytes,
+              cudaStream_t st);
+int tc_kl_wtu(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* Y,
+              int64_t ldy, int64_t m, int64_t n, int k, float eps, int transposed_out, int math_mode, void* ws,
+              int64_t ws_bytes, cudaStream_t st);
+
+}  // namespace dnmf

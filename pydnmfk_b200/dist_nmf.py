@@ -1,0 +1,486 @@
+"""One NMF update step on a 1-D or 2-D processor grid -- device-resident.
+
+Mirrors the public surface of ``pyDNMFk/dist_nmf.py`` (``nmf_algorithms_2D`` :7-579,
+``nmf_algorithms_1D`` :582-1047): same class names, constructor, ``update()`` dispatch and
+error messages, same helper names (``global_gram``, ``global_mm``, ``AH_glob``, ``ATW_glob``,
+``gather_W_H``, ``UHT_glob``, ``WTU_glob``, ``sum_axis`` / ``sum_along_axis``, ``glob_UX``,
+``Fro_MU_update[_W/_H]``, ``KL_MU_update[_W/_H]``, ``FRO_HALS_update[_W/_H]``,
+``FRO_BCD_update``, ``globalSqNorm``, ``initWandH``).
+
+What differs is *where* the arithmetic runs: every numpy expression of the reference is one
+hand-written sm_100a kernel behind ``libdnmf.so`` (see ``device.DeviceOps``), the shard ``A_ij``
+and both factors stay in HBM for the whole fit, the KL path never materialises ``W @ H``,
+and MPI collectives become ``torch.distributed`` (NCCL) collectives on device buffers.  The
+redundant gathers of the reference's 2-D KL/HALS paths are dropped; results are
+unaffected.
+
+Inputs may be numpy arrays (uploaded once per object, results downloaded by ``update()``) or
+CUDA tensors (updated in place, returned as tensors) -- ``PyNMF.fit`` uses the latter.
+"""
+import numpy as np
+import torch
+
+from . import device as D
+from .utils import norm, comm_timing, parse, var_init  # noqa: F401  (re-exported like the reference)
+from .dist_comm import MPI  # noqa: F401
+
+
+def _sqrt_host(t):
+    return float(np.sqrt(t.item()))
+
+
+class _AlgBase:
+    """State shared by the 1-D and 2-D variants."""
+
+    def _setup(self, A_ij, W, H, params):
+        self.params = params
+        self.m, self.n, self.p_r, self.p_c, self.k = params.m, params.n, params.p_r, params.p_c, params.k
+        self.comm1 = params.comm1
+        self.comm = params.comm1
+        self.norm = params.norm
+        self.method = params.method
+        self.eps = params.eps
+        self.p = self.p_r * self.p_c
+        self.W_update = params.W_update
+        self.rank = self.comm1.rank
+        self.ops = D.default_ops()
+        self._A_orig = A_ij
+        self._numpy_io = not isinstance(A_ij, torch.Tensor)
+        self._np_dtype = A_ij.dtype if self._numpy_io else None
+        A = D.to_device(A_ij)
+        return A, D.to_device(W, A.dtype), D.to_device(H, A.dtype)
+
+    def _out(self, W, H):
+        if self._numpy_io:
+            torch.cuda.current_stream().synchronize()
+            return W.cpu().numpy(), H.cpu().numpy()
+        return W, H
+
+    def _dispatch(self):
+        if self.norm.upper() == 'FRO':
+            if self.method.upper() == 'MU':
+                self.Fro_MU_update(self.W_update)
+            elif self.method.upper() == 'HALS':
+                self.FRO_HALS_update(self.W_update)
+            elif self.method.upper() == 'BCD':
+                self.FRO_BCD_update(self.W_update, itr=self.params.itr)
+            else:
+                raise Exception('Not a valid method: Choose (mu/hals/bcd)')
+        elif self.norm.upper() == 'KL':
+            if self.method.upper() == 'MU':
+                self.KL_MU_update(self.W_update)
+            else:
+                raise Exception('Not a valid method: Choose (mu)')
+        else:
+            raise Exception('Not a valid norm: Choose (fro/kl)')
+
+    # ---- BCD scalar logic shared by both grids (dist_nmf.py:503-579, :971-1047) -----------------
+    def _bcd_loop(self, itr):
+        ops = self.ops
+        W, H = self._W(), self._H()
+        Xnorm = self._sqnorm_global(self.A_ij)
+        nW = self._sqnorm_global(W, 'w')
+        nH = self._sqnorm_global(H, 'h')
+        scale = np.sqrt(np.sqrt(Xnorm))
+        W_old = torch.empty_like(W)
+        H_old = torch.empty_like(H)
+        ops.axpby(W_old, W, W, scale / np.sqrt(nW), 0.0)
+        ops.axpby(H_old, H, H, scale / np.sqrt(nH), 0.0)
+        Wm, Hm = W_old.clone(), H_old.clone()
+        HHT = self._gram_H(H_old)
+        AHT = self._AH(H_old)
+        obj_old = 0.5 * Xnorm
+        self.params.rw = 1
+        t_old = 1.0
+        HHTnorm = 1.0
+        WTWnorm = 1.0
+        for _ in range(itr):
+            HHTnorm_old = HHTnorm
+            HHTnorm = _sqrt_host(ops.sqnorm(HHT))
+            ops.bcd_pg_w(W, Wm, AHT, HHT, HHTnorm)
+            wsum = self._colsum_W(W, force=False)
+            ops.div_cols(W, wsum)
+            WTW = self._gram_W(W)
+            WTWnorm_old = WTWnorm
+            WTWnorm = _sqrt_host(ops.sqnorm(WTW))
+            WTA, yT = self._WTA(W)
+            ops.bcd_pg_h(H, Hm, WTA, WTW, WTWnorm, y_transposed=yT)
+            HHT = self._gram_H(H)
+            AHT = self._AH(H)
+            obj = 0.5 * self._residual_global(W, H)[0]
+            t = (1 + np.sqrt(1 + 4 * t_old ** 2)) / 2
+            if obj >= obj_old:
+                Wm.copy_(W_old)
+                Hm.copy_(H_old)
+                HHT = self._gram_H(H_old)
+                AHT = self._AH(H_old)
+            else:
+                w = (t_old - 1) / t
+                ww = min(w, self.params.rw * np.sqrt(HHTnorm_old / HHTnorm))
+                wh = min(w, self.params.rw * np.sqrt(WTWnorm_old / WTWnorm))
+                ops.axpby(Wm, W, W_old, 1.0 + ww, -ww)
+                ops.axpby(Hm, H, H_old, 1.0 + wh, -wh)
+                W_old.copy_(W)
+                H_old.copy_(H)
+                t_old = t
+                obj_old = obj
+
+
+class nmf_algorithms_2D(_AlgBase):
+    """Distributed NMF step on a 2-D p_r x p_c grid (dist_nmf.py:7-579).
+
+    Per rank: ``A_ij`` (m/p_r x n/p_c), ``W_ij`` (m/p x k), ``H_ij`` (k x n/p)."""
+
+    @comm_timing()
+    def __init__(self, A_ij, W_ij, H_ij, params=None):
+        self.A_ij, self.W_ij, self.H_ij = self._setup(A_ij, W_ij, H_ij, params)
+        self.cartesian1d_row, self.cartesian1d_column = params.row_comm, params.col_comm
+        self.comm = params.comm
+        self.local_W_m = self.W_ij.shape[0]
+        self.local_H_n = self.H_ij.shape[1]
+        # shard sizes of every member (ragged grids / pruned shards): exchanged once, integers
+        self._w_sizes = [int(s) for s in self.cartesian1d_column.allgather(int(self.local_W_m))]
+        self._h_sizes = [int(s) for s in self.cartesian1d_row.allgather(int(self.local_H_n))]
+        self.W_i = None
+        self.H_j = None
+
+    def _W(self):
+        return self.W_ij
+
+    def _H(self):
+        return self.H_ij
+
+    def update(self):
+        """One update of W_ij and H_ij (dist_nmf.py:66-92)."""
+        self._dispatch()
+        return self._out(self.W_ij, self.H_ij)
+
+    # ---- distributed building blocks -------------------------------------------------------
+    @comm_timing()
+    def global_gram(self, A):
+        """A^T A summed over all ranks (dist_nmf.py:94-116); ``A`` is W_ij or H_ij.T."""
+        A = D.to_device_view(A, self.A_ij.dtype)
+        G = self.ops.gram(A, trans=False) if A.is_contiguous() else self.ops.gram(A.t().contiguous(), trans=True)
+        return self.comm1.allreduce_(G)
+
+    def _gram_W(self, W):
+        return self.comm1.allreduce_(self.ops.gram(W, trans=False))
+
+    def _gram_H(self, H):
+        return self.comm1.allreduce_(self.ops.gram(H, trans=True))
+
+    @comm_timing()
+    def gather_W_H(self, gW=True, gH=True):
+        """H_ij -> H_j over the row communicator, W_ij -> W_i over the column communicator
+        (dist_nmf.py:267-291)."""
+        if gH:
+            self.H_j = self._gather_H(self.H_ij)
+        if gW:
+            self.W_i = self._gather_W(self.W_ij)
+
+    def _gather_H(self, H_ij):
+        # gather the transposed shards (n_loc x k): concatenation along rows == hstack of H shards
+        Ht = self.cartesian1d_row.allgather_cat(H_ij.t().contiguous(), self._h_sizes)
+        return Ht.t().contiguous()
+
+    def _gather_W(self, W_ij):
+        return self.cartesian1d_column.allgather_cat(W_ij, self._w_sizes)
+
+    def _AH(self, H_ij):
+        H_j = self._gather_H(H_ij)
+        V = self.ops.ah(self.A_ij, H_j)
+        return self.cartesian1d_column.reduce_scatter_rows(V, self._w_sizes)
+
+    def _WTA(self, W_ij):
+        W_i = self._gather_W(W_ij)
+        Yt = self.ops.wta(self.A_ij, W_i, transposed_out=True)
+        return self.cartesian1d_row.reduce_scatter_rows(Yt, self._h_sizes), True
+
+    @comm_timing()
+    def AH_glob(self, H_ij=None):
+        """A H^T: allgather(row comm) -> skinny GEMM -> reduce-scatter(column comm) (dist_nmf.py:174-205)."""
+        return self._AH(self.H_ij if H_ij is None else D.to_device(H_ij, self.A_ij.dtype))
+
+    @comm_timing()
+    def ATW_glob(self):
+        """W^T A as a k x n/p view: allgather(column comm) -> skinny GEMM emitted directly in the
+        transposed reduce-scatter layout -> reduce-scatter(row comm) (dist_nmf.py:144-172)."""
+        Yt, _ = self._WTA(self.W_ij)
+        return Yt.t()
+
+    @comm_timing()
+    def UHT_glob(self):
+        """(A / (W_i H_j + eps)) H_j^T, fused, then reduce-scatter (dist_nmf.py:320-343)."""
+        V = self.ops.kl_uht(self.A_ij, self.W_i, self.H_j, self.eps)
+        return self.cartesian1d_column.reduce_scatter_rows(V, self._w_sizes)
+
+    @comm_timing()
+    def WTU_glob(self):
+        """W_i^T (A / (W_i H_j + eps)), fused, then reduce-scatter (dist_nmf.py:293-318)."""
+        Yt = self.ops.kl_wtu(self.A_ij, self.W_i, self.H_j, self.eps, transposed_out=True)
+        return self.cartesian1d_row.reduce_scatter_rows(Yt, self._h_sizes).t()
+
+    @comm_timing()
+    def sum_axis(self, dat, axis):
+        """dat.sum(axis) all-reduced over the world (dist_nmf.py:345-349)."""
+        s = self.ops.colsum(dat) if axis == 0 else self.ops.rowsum(dat)
+        return self.comm1.allreduce_(s)
+
+    # ---- FRO / MU -----------------------------------------------------------------------------
+    def Fro_MU_update_H(self):
+        """dist_nmf.py:207-225."""
+        W_TW = self._gram_W(self.W_ij)
+        Yt, _ = self._WTA(self.W_ij)
+        self.ops.mu_update_h(self.H_ij, Yt, W_TW, self.eps, y_transposed=True)
+
+    def Fro_MU_update_W(self):
+        """dist_nmf.py:227-245."""
+        HH_T = self._gram_H(self.H_ij)
+        AH = self._AH(self.H_ij)
+        self.ops.mu_update_w(self.W_ij, AH, HH_T, self.eps)
+
+    def Fro_MU_update(self, W_update=True):
+        """dist_nmf.py:247-263: W first, then H with the new W."""
+        if W_update == True:  # noqa: E712 (same test as the reference)
+            self.Fro_MU_update_W()
+        self.Fro_MU_update_H()
+
+    # ---- KL / MU ------------------------------------------------------------------------------
+    def KL_MU_update_W(self):
+        """dist_nmf.py:351-369."""
+        x2 = self.sum_axis(self.H_ij, axis=1)
+        self.gather_W_H()
+        sk = self.UHT_glob()
+        self.ops.kl_update_w(self.W_ij, sk, x2, self.eps)
+
+    def KL_MU_update_H(self):
+        """dist_nmf.py:371-389."""
+        x1 = self.sum_axis(self.W_ij, axis=0)
+        self.gather_W_H()
+        Yt = self.ops.kl_wtu(self.A_ij, self.W_i, self.H_j, self.eps, transposed_out=True)
+        Yt = self.cartesian1d_row.reduce_scatter_rows(Yt, self._h_sizes)
+        self.ops.kl_update_h(self.H_ij, Yt, x1, self.eps, y_transposed=True)
+
+    def KL_MU_update(self, W_update=True):
+        """dist_nmf.py:391-407."""
+        if W_update == True:  # noqa: E712
+            self.KL_MU_update_W()
+        self.KL_MU_update_H()
+
+    # ---- FRO / HALS -----------------------------------------------------------------------------
+    def FRO_HALS_update_W(self):
+        """dist_nmf.py:411-432: Gauss-Seidel over columns, global column norm after each."""
+        HHT = self._gram_H(self.H_ij)
+        AH = self._AH(self.H_ij)
+        for kk in range(self.k):
+            sq = self.ops.hals_w_col(self.W_ij, AH, HHT, kk, self.eps)
+            if self.p_r != 1:
+                sq = self.comm1.allreduce_(sq)
+            self.ops.div_col(self.W_ij, kk, sq)
+
+    def FRO_HALS_update_H(self):
+        """dist_nmf.py:434-452."""
+        WTW = self._gram_W(self.W_ij)
+        Yt, _ = self._WTA(self.W_ij)
+        self.ops.hals_h(self.H_ij, Yt, WTW, self.eps, y_transposed=True)
+
+    def FRO_HALS_update(self, W_update=True):
+        """dist_nmf.py:454-470."""
+        if W_update == True:  # noqa: E712
+            self.FRO_HALS_update_W()
+        self.FRO_HALS_update_H()
+
+    # ---- FRO / BCD ------------------------------------------------------------------------------
+    def _sqnorm_global(self, X, which=None):
+        return float(self.comm1.allreduce_(self.ops.sqnorm(X)).item())
+
+    @comm_timing()
+    def globalSqNorm(self, comm, X):
+        """Global squared Frobenius norm (dist_nmf.py:474-480)."""
+        return self._sqnorm_global(D.to_device(X, self.A_ij.dtype))
+
+    def _colsum_W(self, W, force):
+        return self.comm1.allreduce_(self.ops.colsum(W))
+
+    def _residual_global(self, W, H):
+        W_i, H_j = self._gather_W(W), self._gather_H(H)
+        r = self.comm1.allreduce_(self.ops.residual_sqnorm(self.A_ij, W_i, H_j))
+        return r.cpu().numpy()
+
+    def initWandH(self):
+        raise NotImplementedError('folded into FRO_BCD_update (dist_nmf.py:482-501)')
+
+    def FRO_BCD_update(self, W_update=True, itr=1000):
+        """dist_nmf.py:503-579 (its own ``itr`` loop; ignores W_update)."""
+        self._bcd_loop(itr)
+
+
+class nmf_algorithms_1D(_AlgBase):
+    """Distributed NMF step on a 1-D grid (dist_nmf.py:582-1047).
+
+    Row grid (p_c = 1): ``A_ij`` is an m/p_r x n block, ``W_i`` its m/p_r x k rows, ``H_j``
+    (k x n) is replicated.  Column grid (p_r = 1) is the mirror image."""
+
+    def __init__(self, A_ij, W_i, H_j, params=None):
+        self.A_ij, self.W_i, self.H_j = self._setup(A_ij, W_i, H_j, params)
+        self.local_W_m = self.W_i.shape[0]
+        self.local_H_n = self.H_j.shape[1]
+
+    def _W(self):
+        return self.W_i
+
+    def _H(self):
+        return self.H_j
+
+    def update(self):
+        """One update of W_i and H_j (dist_nmf.py:634-660)."""
+        self._dispatch()
+        return self._out(self.W_i, self.H_j)
+
+    # ---- distributed building blocks -------------------------------------------------------
+    @comm_timing()
+    def global_gram(self, A, p=1):
+        """A^T A, all-reduced iff p != 1 (dist_nmf.py:662-685)."""
+        A = D.to_device_view(A, self.A_ij.dtype)
+        G = self.ops.gram(A, trans=False) if A.is_contiguous() else self.ops.gram(A.t().contiguous(), trans=True)
+        return self.comm1.allreduce_(G) if p != 1 else G
+
+    @comm_timing()
+    def global_mm(self, A, B, p=-1):
+        """Only the two A-streaming products of the update loop are supported:
+        ``global_mm(A_ij, H_j.T, p_c)`` and ``global_mm(W_i.T, A_ij, p_r)`` (dist_nmf.py:687-711)."""
+        if A is self.A_ij or A is self._A_orig:
+            out = self.ops.ah(self.A_ij, D.to_device_view(B, self.A_ij.dtype).t().contiguous())
+        elif B is self.A_ij or B is self._A_orig:
+            out = self.ops.wta(self.A_ij, D.to_device_view(A, self.A_ij.dtype).t().contiguous())
+        else:
+            raise NotImplementedError('global_mm: one operand must be the resident shard A_ij')
+        return self.comm1.allreduce_(out) if p != 1 else out
+
+    def _gram_W(self, W):
+        G = self.ops.gram(W, trans=False)
+        return self.comm1.allreduce_(G) if self.p_r != 1 else G
+
+    def _gram_H(self, H):
+        G = self.ops.gram(H, trans=True)
+        return self.comm1.allreduce_(G) if self.p_c != 1 else G
+
+    def _AH(self, H):
+        V = self.ops.ah(self.A_ij, H)
+        return self.comm1.allreduce_(V) if self.p_c != 1 else V
+
+    def _WTA(self, W):
+        Y = self.ops.wta(self.A_ij, W)
+        return (self.comm1.allreduce_(Y) if self.p_r != 1 else Y), False
+
+    # ---- FRO / MU -----------------------------------------------------------------------------
+    @comm_timing()
+    def Fro_MU_update_W(self):
+        """dist_nmf.py:715-732."""
+        HH_T = self._gram_H(self.H_j)
+        AH = self._AH(self.H_j)
+        self.ops.mu_update_w(self.W_i, AH, HH_T, self.eps)
+
+    @comm_timing()
+    def Fro_MU_update_H(self):
+        """dist_nmf.py:735-751."""
+        W_TW = self._gram_W(self.W_i)
+        AtW, _ = self._WTA(self.W_i)
+        self.ops.mu_update_h(self.H_j, AtW, W_TW, self.eps)
+
+    @comm_timing()
+    def Fro_MU_update(self, W_update=True):
+        """dist_nmf.py:754-771."""
+        if W_update == True:  # noqa: E712
+            self.Fro_MU_update_W()
+        self.Fro_MU_update_H()
+
+    # ---- KL / MU ------------------------------------------------------------------------------
+    @comm_timing()
+    def sum_along_axis(self, X, p=1, axis=0):
+        """dist_nmf.py:775-801."""
+        X = D.to_device(X, self.A_ij.dtype)
+        s = self.ops.colsum(X) if axis == 0 else self.ops.rowsum(X)
+        return self.comm1.allreduce_(s) if p != 1 else s
+
+    @comm_timing()
+    def glob_UX(self, axis):
+        """Fused ``A / (W H + eps)`` contraction (dist_nmf.py:803-811); no m x n temporaries."""
+        if axis == 1:
+            UX = self.ops.kl_wtu(self.A_ij, self.W_i, self.H_j, self.eps)
+            return self.comm1.allreduce_(UX) if self.p_r != 1 else UX
+        elif axis == 0:
+            UX = self.ops.kl_uht(self.A_ij, self.W_i, self.H_j, self.eps)
+            return self.comm1.allreduce_(UX) if self.p_c != 1 else UX
+
+    def KL_MU_update_W(self):
+        """dist_nmf.py:813-830."""
+        x2 = self.sum_along_axis(self.H_j, p=self.p_c, axis=1)
+        sk = self.glob_UX(axis=0)
+        self.ops.kl_update_w(self.W_i, sk, x2, self.eps)
+
+    def KL_MU_update_H(self):
+        """dist_nmf.py:832-849."""
+        x2 = self.sum_along_axis(self.W_i, p=self.p_r, axis=0)
+        sk = self.glob_UX(axis=1)
+        self.ops.kl_update_h(self.H_j, sk, x2, self.eps)
+
+    def KL_MU_update(self, W_update=True):
+        """dist_nmf.py:851-869."""
+        if W_update == True:  # noqa: E712
+            self.KL_MU_update_W()
+        self.KL_MU_update_H()
+
+    # ---- FRO / HALS -----------------------------------------------------------------------------
+    def FRO_HALS_update_W(self):
+        """dist_nmf.py:873-893."""
+        HHT = self._gram_H(self.H_j)
+        AH = self._AH(self.H_j)
+        for kk in range(self.k):
+            sq = self.ops.hals_w_col(self.W_i, AH, HHT, kk, self.eps)
+            if self.p_r != 1:
+                sq = self.comm1.allreduce_(sq)
+            self.ops.div_col(self.W_i, kk, sq)
+
+    def FRO_HALS_update_H(self):
+        """dist_nmf.py:895-913."""
+        WTW = self._gram_W(self.W_i)
+        AtW, _ = self._WTA(self.W_i)
+        self.ops.hals_h(self.H_j, AtW, WTW, self.eps)
+
+    def FRO_HALS_update(self, W_update=True):
+        """dist_nmf.py:916-934."""
+        if W_update == True:  # noqa: E712
+            self.FRO_HALS_update_W()
+        self.FRO_HALS_update_H()
+
+    # ---- FRO / BCD ------------------------------------------------------------------------------
+    def _sqnorm_global(self, X, which=None):
+        sq = self.ops.sqnorm(X)
+        p = {None: -1, 'w': self.p_r, 'h': self.p_c}[which]
+        if p != 1:
+            sq = self.comm1.allreduce_(sq)
+        return float(sq.item())
+
+    @comm_timing()
+    def globalSqNorm(self, X, p=-1):
+        """dist_nmf.py:939-949."""
+        sq = self.ops.sqnorm(D.to_device(X, self.A_ij.dtype))
+        if p != 1:
+            sq = self.comm1.allreduce_(sq)
+        return float(sq.item())
+
+    def _colsum_W(self, W, force):
+        s = self.ops.colsum(W)
+        return self.comm1.allreduce_(s) if self.p_r != 1 else s
+
+    def _residual_global(self, W, H):
+        r = self.comm1.allreduce_(self.ops.residual_sqnorm(self.A_ij, W, H))
+        return r.cpu().numpy()
+
+    def initWandH(self):
+        raise NotImplementedError('folded into FRO_BCD_update (dist_nmf.py:951-969)')
+
+    def FRO_BCD_update(self, W_update=True, itr=1000):
+        """dist_nmf.py:971-1047."""
+        self._bcd_loop(itr)
