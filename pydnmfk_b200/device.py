@@ -75,6 +75,27 @@ class DeviceOps:
         self.math_mode = math_mode
         self._ws = None
         self._ws_bytes = 0
+        self.timers = None      # set to {} to bracket the A-streaming passes with CUDA events (bench.py)
+
+    def _t0(self, name):
+        if self.timers is None:
+            return None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record(torch.cuda.current_stream(self.device))
+        self.timers.setdefault(name, []).append(ev)
+        return ev
+
+    def _t1(self, ev):
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(self.device))
+
+    def timer_summary(self):
+        """{op: (launches, mean ms)} from the recorded events (call after a synchronize)."""
+        out = {}
+        for name, evs in (self.timers or {}).items():
+            ms = [a.elapsed_time(b) for a, b in evs]
+            out[name] = (len(ms), sum(ms) / max(len(ms), 1))
+        return out
 
     # ---- plumbing -------------------------------------------------------------------------
     def _stream(self):
@@ -101,8 +122,10 @@ class DeviceOps:
         dt = _DT[A.dtype]
         V = out if out is not None else self.empty((m, k), A.dtype)
         ws, wsb = self._ws_for(L.OP_AH, m, n, k, dt)
+        ev = self._t0('ah')
         L.call('dnmf_ah', A.data_ptr(), _ld(A), H.data_ptr(), _ld(H), V.data_ptr(), _ld(V), m, n, k, dt,
                self.math_mode, ws, wsb, self._stream())
+        self._t1(ev)
         return V
 
     def wta(self, A, W, transposed_out=False, out=None):
@@ -112,8 +135,10 @@ class DeviceOps:
         dt = _DT[A.dtype]
         Y = out if out is not None else self.empty((n, k) if transposed_out else (k, n), A.dtype)
         ws, wsb = self._ws_for(L.OP_WTA, m, n, k, dt)
+        ev = self._t0('wta')
         L.call('dnmf_wta', A.data_ptr(), _ld(A), W.data_ptr(), _ld(W), Y.data_ptr(), _ld(Y), m, n, k,
                1 if transposed_out else 0, dt, self.math_mode, ws, wsb, self._stream())
+        self._t1(ev)
         return Y
 
     def kl_uht(self, A, W, H, eps, out=None):
@@ -123,8 +148,10 @@ class DeviceOps:
         dt = _DT[A.dtype]
         V = out if out is not None else self.empty((m, k), A.dtype)
         ws, wsb = self._ws_for(L.OP_KL_UHT, m, n, k, dt)
+        ev = self._t0('kl_uht')
         L.call('dnmf_kl_uht', A.data_ptr(), _ld(A), W.data_ptr(), _ld(W), H.data_ptr(), _ld(H), V.data_ptr(),
                _ld(V), m, n, k, float(eps), dt, self.math_mode, ws, wsb, self._stream())
+        self._t1(ev)
         return V
 
     def kl_wtu(self, A, W, H, eps, transposed_out=False, out=None):
@@ -134,9 +161,11 @@ class DeviceOps:
         dt = _DT[A.dtype]
         Y = out if out is not None else self.empty((n, k) if transposed_out else (k, n), A.dtype)
         ws, wsb = self._ws_for(L.OP_KL_WTU, m, n, k, dt)
+        ev = self._t0('kl_wtu')
         L.call('dnmf_kl_wtu', A.data_ptr(), _ld(A), W.data_ptr(), _ld(W), H.data_ptr(), _ld(H), Y.data_ptr(),
                _ld(Y), m, n, k, float(eps), 1 if transposed_out else 0, dt, self.math_mode, ws, wsb,
                self._stream())
+        self._t1(ev)
         return Y
 
     def gram(self, X, trans):

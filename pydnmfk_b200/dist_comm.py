@@ -42,7 +42,11 @@ def _ensure_world():
     if torch.cuda.is_available():
         ndev = torch.cuda.device_count()
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0'))) % ndev)
-    dist.init_process_group(backend=backend, rank=int(os.environ['RANK']), world_size=ws)
+    kw = {}
+    if os.environ.get('DNMF_PG_TIMEOUT_S'):
+        import datetime
+        kw['timeout'] = datetime.timedelta(seconds=int(os.environ['DNMF_PG_TIMEOUT_S']))
+    dist.init_process_group(backend=backend, rank=int(os.environ['RANK']), world_size=ws, **kw)
     return True
 
 

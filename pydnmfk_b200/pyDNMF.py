@@ -21,6 +21,23 @@ from .utils import data_operations, determine_block_params, var_init, comm_timin
 from .dist_comm import MPI
 
 
+def draw_rand_factors(topo, p_c, rank, a_shape, factor_shape, k, dt):
+    """Host draws of the 'rand' initialisation in the reference's exact order (pyDNMF.py:110-129):
+    2-D: W_ij = rand(m_loc, k) then H_ij = rand(k, n_loc) on every rank; 1-D row grid: W_i on every
+    rank, then the replicated H on rank 0 only; 1-D column grid mirrored.  Returns (W, H) with None
+    for a replicated factor this rank must receive by broadcast."""
+    if topo == '2d':
+        W = np.random.rand(factor_shape[0], k).astype(dt)
+        H = np.random.rand(k, factor_shape[1]).astype(dt)
+    elif p_c == 1:
+        W = np.random.rand(a_shape[0], k).astype(dt)
+        H = np.random.rand(k, a_shape[1]).astype(dt) if rank == 0 else None
+    else:
+        H = np.random.rand(k, a_shape[1]).astype(dt)
+        W = np.random.rand(a_shape[0], k).astype(dt) if rank == 0 else None
+    return W, H
+
+
 class PyNMF():
     r"""Distributed NMF decomposition of the matrix whose local shard is ``A_ij``.
 
@@ -96,17 +113,13 @@ class PyNMF():
         the reference's starting point bit for bit."""
         dt = self._np_dtype
         if self.init == 'rand':
-            if self.topo == '2d':
-                W = np.random.rand(self.params.m_loc, self.k).astype(dt)
-                H = np.random.rand(self.k, self.params.n_loc).astype(dt)
-            elif self.p_c == 1:
-                W = np.random.rand(self.m_loc, self.k).astype(dt)
-                H = np.random.rand(self.k, self.n_loc).astype(dt) if self.rank == 0 else None
-                H = self._bcast_factor(H, (self.k, self.n_loc))
-            else:  # p_r == 1
-                H = np.random.rand(self.k, self.n_loc).astype(dt)
-                W = np.random.rand(self.m_loc, self.k).astype(dt) if self.rank == 0 else None
-                W = self._bcast_factor(W, (self.m_loc, self.k))
+            W, H = draw_rand_factors(self.topo, self.p_c, self.rank, (self.m_loc, self.n_loc),
+                                     (self.params.m_loc, self.params.n_loc), self.k, dt)
+            if self.topo == '1d':
+                if self.p_c == 1:
+                    H = self._bcast_factor(H, (self.k, self.n_loc))
+                else:
+                    W = self._bcast_factor(W, (self.m_loc, self.k))
             return D.to_device(W, self._tdtype), D.to_device(H, self._tdtype)
         elif self.init == 'nnsvd':
             if self.topo == '1d':

@@ -1,0 +1,83 @@
+"""Host-side logic that needs no GPU: shard index maps, argument helpers, error messages."""
+import numpy as np
+import pytest
+
+from oracle import nmf_oracle as O
+from tests import common as T
+
+
+def test_determine_block_params_known_answers():
+    from pydnmfk_b200.utils import determine_block_params
+    # the reference's own known-answer test (tests/test_dist_file_split.py:26-30)
+    d0 = determine_block_params(0, (2, 1), (96, 21))
+    d1 = determine_block_params(1, (2, 1), (96, 21))
+    assert d0.determine_block_index_range_asymm() == ([0, 0], [47, 20])
+    assert d0.determine_block_shape_asymm() == [48, 21]
+    assert d1.determine_block_index_range_asymm() == ([48, 0], [95, 20])
+    assert d1.determine_block_shape_asymm() == [48, 21]
+    aux = T.golden('aux_cases.npz')
+    n = 0
+    for key, val in aux.items():
+        if not key.startswith('blocks/'):
+            continue
+        shape = tuple(int(v) for v in key.split('/')[1].split('x'))
+        grid = tuple(int(v) for v in key.split('/')[2].split('x'))
+        for r in range(grid[0] * grid[1]):
+            d = determine_block_params(r, grid, shape)
+            s, e = d.determine_block_index_range_asymm()
+            assert list(s) + list(e) + d.determine_block_shape_asymm() == [int(v) for v in val[r]]
+            n += 1
+    assert n > 30
+
+
+def test_block_params_match_oracle_on_random_shapes():
+    from pydnmfk_b200.utils import determine_block_params
+    rs = np.random.RandomState(0)
+    for _ in range(200):
+        grid = (int(rs.randint(1, 7)), int(rs.randint(1, 7)))
+        shape = (int(rs.randint(grid[0], 500)), int(rs.randint(grid[1], 500)))
+        for r in range(grid[0] * grid[1]):
+            d = determine_block_params(r, grid, shape)
+            s, e = d.determine_block_index_range_asymm()
+            so, eo = O.block_range(r, grid, shape)
+            assert (list(s), list(e)) == (so, eo)
+
+
+def test_arg_helpers():
+    from pydnmfk_b200.utils import parse, var_init, str2bool
+    p = parse()
+    assert var_init(p, 'norm', 'kl') == 'kl' and p.norm == 'kl'
+    p.norm = 'fro'
+    assert var_init(p, 'norm', 'kl') == 'fro'
+    assert str2bool('Yes') is True and str2bool('0') is False and str2bool(True) is True
+    with pytest.raises(NameError, match='Boolean value expected.'):
+        str2bool('maybe')
+
+
+def test_single_process_comm_is_a_noop_world():
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm
+    comm = MPI.COMM_WORLD
+    assert comm.size == 1 and comm.rank == 0 and comm.Get_rank() == 0 and comm.Get_size() == 1
+    comms = MPI_comm(comm, 1, 1)
+    assert comms.coord2d == [0, 0]
+    row, col = comms.cart_1d_row(), comms.cart_1d_column()
+    assert row.size == 1 and col.size == 1
+    assert comm.allreduce(5) == 5
+    x = np.arange(4.0)
+    assert np.array_equal(comm.allreduce(x), x)
+    assert comm.allgather('a') == ['a']
+    assert comm.bcast({'k': 1}, root=0) == {'k': 1}
+    comm.barrier()
+    comms.Free()
+
+
+def test_data_operations_dims_single_rank():
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm
+    from pydnmfk_b200.utils import parse, data_operations
+    comm = MPI.COMM_WORLD
+    comms = MPI_comm(comm, 1, 1)
+    p = parse()
+    p.comm1, p.row_comm, p.col_comm, p.p_r, p.p_c, p.topo, p.k = comm, comms.cart_1d_row(), comms.cart_1d_column(), 1, 1, '1d', 3
+    A = np.zeros((26, 14), dtype=np.float32)
+    data_operations(A, p)
+    assert (p.m, p.n, p.m_loc, p.n_loc, p.W_start, p.W_end, p.H_start, p.H_end) == (26, 14, 26, 14, 0, 26, 0, 14)

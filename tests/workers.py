@@ -1,0 +1,127 @@
+"""Module-level rank functions for tests/mp_util.run (they must be importable by spawned processes)."""
+import numpy as np
+
+
+def comm_worker(rank, world, p_r, p_c):
+    """Exercise every collective of pydnmfk_b200.dist_comm on CPU tensors / numpy / scalars."""
+    import torch
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm
+    comm = MPI.COMM_WORLD
+    assert comm.size == world and comm.rank == rank
+    comms = MPI_comm(comm, p_r, p_c)
+    row, col = comms.cart_1d_row(), comms.cart_1d_column()
+    i, j = divmod(rank, p_c)
+    out = dict(coord=comms.coord2d, row_ranks=row.ranks, col_ranks=col.ranks, row_rank=row.rank, col_rank=col.rank)
+    out['sum_int'] = comm.allreduce(rank + 1)
+    out['sum_arr'] = comm.allreduce(np.full((2, 3), rank + 1.0, dtype=np.float32))
+    out['row_sum'] = row.allreduce(np.array([10.0 * i + j]))
+    out['col_sum'] = col.allreduce(np.array([10.0 * i + j]))
+    out['gather'] = comm.allgather(('r', rank))
+    out['bcast'] = comm.bcast({'from': rank} if rank == 0 else None, root=0)
+    t = torch.full((4,), float(rank), dtype=torch.float64)
+    out['t_allreduce'] = comm.allreduce_(t.clone()).numpy()
+    out['t_gather'] = col.allgather_cat(torch.full((2, 3), float(rank))).numpy()
+    sizes = [q + 1 for q in range(row.size)]
+    out['t_gather_ragged'] = row.allgather_cat(torch.full((row.rank + 1, 2), float(rank)), sizes).numpy()
+    full = torch.arange(float(row.size * 2 * 3)).reshape(row.size * 2, 3) * (rank + 1)
+    out['t_rs'] = row.reduce_scatter_rows(full).numpy()
+    rag = [1 + q for q in range(col.size)]
+    full2 = torch.arange(float(sum(rag) * 2)).reshape(sum(rag), 2) * (rank + 1)
+    out['t_rs_ragged'] = col.reduce_scatter_rows(full2, rag).numpy()
+    b = torch.full((3,), float(rank + 5))
+    out['t_bcast'] = comm.bcast_(b, root=0).numpy()
+    send = np.arange(float(world * 3)) * (rank + 1)
+    recv = np.empty(3)
+    comm.Reduce_scatter(send, recv)
+    out['Reduce_scatter'] = recv
+    buf = np.full(4, float(rank))
+    comm.Bcast(buf, root=world - 1)
+    out['Bcast'] = buf
+    comm.barrier()
+    comms.Free()
+    return out
+
+
+def dims_worker(rank, world, case):
+    """data_operations geometry + the RNG order of the rand initialisation, on the host."""
+    from oracle import cases as C
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm
+    from pydnmfk_b200.utils import parse, data_operations, determine_block_params
+    from pydnmfk_b200.pyDNMF import draw_rand_factors
+    p_r, p_c = case['grid']
+    comm = MPI.COMM_WORLD
+    comms = MPI_comm(comm, p_r, p_c)
+    np.random.seed(case['seed'])
+    A = C.draw_global(case, np.random)
+    blk = determine_block_params(rank, (p_r, p_c), A.shape).determine_block_index_range_asymm()
+    A_ij = A[blk[0][0]:blk[1][0] + 1, blk[0][1]:blk[1][1] + 1]
+    p = parse()
+    p.comm1, p.row_comm, p.col_comm, p.p_r, p.p_c, p.k = comm, comms.cart_1d_row(), comms.cart_1d_column(), p_r, p_c, case['k']
+    p.topo = '2d' if (p_r != 1 and p_c != 1) else '1d'
+    data_operations(A_ij, p)
+    W, H = draw_rand_factors(p.topo, p_c, rank, A_ij.shape, (p.m_loc, p.n_loc), case['k'], A_ij.dtype)
+    if p.topo == '1d':
+        if p_c == 1:
+            H = comm.bcast(H, root=0)
+        else:
+            W = comm.bcast(W, root=0)
+    geom = [p.m, p.n, p.m_loc, p.n_loc, p.W_start, p.W_end, p.H_start, p.H_end, blk[0][0], blk[1][0], blk[0][1], blk[1][1]]
+    return dict(geom=[int(v) for v in geom], W=W, H=H)
+
+
+def fit_worker(rank, world, case, force_generic=False):
+    """One PyNMF.fit of a parity case on this rank (GPU; several ranks may share cuda:0 via gloo)."""
+    import torch
+    from oracle import cases as C
+    from pydnmfk_b200 import _lib as L
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm
+    from pydnmfk_b200.utils import parse, determine_block_params, data_operations
+    from pydnmfk_b200.pyDNMF import PyNMF
+    torch.cuda.set_device(0)
+    L.set_force_generic(force_generic)
+    p_r, p_c = case['grid']
+    comm = MPI.COMM_WORLD
+    comms = MPI_comm(comm, p_r, p_c)
+    np.random.seed(case['seed'])
+    A = C.draw_global(case, np.random)
+    args = parse()
+    args.size, args.rank, args.comm1, args.comm, args.p_r, args.p_c = world, rank, comms.comm, comms, p_r, p_c
+    args.m, args.n, args.k = case['m'], case['n'], case['k']
+    args.itr, args.init, args.verbose = case['itr'], 'rand', False
+    args.row_comm, args.col_comm = comms.cart_1d_row(), comms.cart_1d_column()
+    args.norm, args.method, args.prune = case['norm'], case['method'], case['prune']
+    args.W_update = case['W_update']
+    blk = determine_block_params(rank, (p_r, p_c), A.shape).determine_block_index_range_asymm()
+    A_ij = np.ascontiguousarray(A[blk[0][0]:blk[1][0] + 1, blk[0][1]:blk[1][1] + 1])
+    factors = None
+    if case['given_factors']:
+        args.topo = '2d' if (p_r != 1 and p_c != 1) else '1d'
+        dop = data_operations(A_ij, args)
+        ml, nl = (dop.params.m_loc, dop.params.n_loc) if args.topo == '2d' else A_ij.shape
+        factors = list(C.draw_given_factors(case, np.random, ml, nl))
+    W, H, err = PyNMF(A_ij, factors=factors, params=args).fit()
+    out = dict(W=np.asarray(W), H=np.asarray(H), err=float(err), err_dtype=str(np.asarray(err).dtype),
+               geom=[int(v) for v in (args.m, args.n, args.m_loc, args.n_loc, args.W_start, args.W_end,
+                                      args.H_start, args.H_end)])
+    if case['prune']:
+        out.update(row_zero_idx_x=np.asarray(args.row_zero_idx_x), col_zero_idx_x=np.asarray(args.col_zero_idx_x),
+                   row_zero_idx_w=np.asarray(args.row_zero_idx_w), col_zero_idx_h=np.asarray(args.col_zero_idx_h))
+    return out
+
+
+def fit_many_worker(rank, world, cases, force_generic=False):
+    """Several parity cases (same world size, any grid) in one process group: amortises process spawn
+    and CUDA context creation.  Per-case failures are captured, not raised."""
+    import traceback
+    out = {}
+    for case in cases:
+        try:
+            out[case['name']] = ('ok', fit_worker(rank, world, case, force_generic))
+            ok = 1
+        except BaseException:
+            out[case['name']] = ('err', traceback.format_exc())
+            ok = 0
+        from pydnmfk_b200.dist_comm import MPI
+        if MPI.COMM_WORLD.allreduce(ok) != world:
+            break   # stop the batch on every rank together
+    return out
