@@ -64,6 +64,8 @@ int64_t dnmf_launch_count(int reset);
 int dnmf_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* 0 = auto (tcgen05 when eligible), 1 = force generic kernels */
 int dnmf_set_force_generic(int on);
+/* smallest shard (m*n elements) routed to the tcgen05 path; default 2^20, tests lower it */
+int dnmf_set_tc_min_elems(int64_t elems);
 
 int64_t dnmf_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype);
 

@@ -25,6 +25,7 @@ SIGNATURES = {
     'dnmf_launch_count': (i64, [i32]),
     'dnmf_device_info': (i32, [C.POINTER(i32)] * 3),
     'dnmf_set_force_generic': (i32, [i32]),
+    'dnmf_set_tc_min_elems': (i32, [i64]),
     'dnmf_workspace_bytes': (i64, [i32, i64, i64, i64, i32]),
     'dnmf_ah': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, i32, vp, i64, vp]),
     'dnmf_wta': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, i32, i32, vp, i64, vp]),
@@ -57,7 +58,7 @@ SIGNATURES = {
 }
 
 _NO_STATUS = {'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
-              'dnmf_set_force_generic'}
+              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems'}
 
 
 class DnmfError(RuntimeError):
@@ -115,3 +116,7 @@ def launch_count(reset=False):
 
 def set_force_generic(on):
     _lib.dnmf_set_force_generic(1 if on else 0)
+
+
+def set_tc_min_elems(elems):
+    _lib.dnmf_set_tc_min_elems(int(elems))

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "tc_api.cuh"
 
 namespace dnmf {
 
@@ -72,6 +73,11 @@ int64_t dnmf_launch_count(int reset) {
 
 int dnmf_set_force_generic(int on) {
   tls().force_generic = on ? 1 : 0;
+  return 0;
+}
+
+int dnmf_set_tc_min_elems(int64_t elems) {
+  tc_set_min_elems(elems);
   return 0;
 }
 

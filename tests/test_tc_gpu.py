@@ -1,0 +1,110 @@
+"""The tcgen05 / TMA / TMEM path of the A-streaming contractions (fp32, k in {16, 32, 64}).
+
+Checked three ways: bit-exact on small-integer data (every product and partial sum is exact in tf32/fp32, so
+any descriptor / swizzle / layout mistake shows up as a hard mismatch), against float64 numpy on random data
+(the 3-term tf32 split must deliver fp32-level accuracy), and against the generic CUDA-core kernels.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 32, 16), (128, 64, 32), (256, 96, 64), (1000, 1000, 32), (515, 2052, 32), (2048, 2048, 32),
+          (4100, 300, 64), (3000, 5000, 16), (1024, 8192, 32), (8192, 1024, 32), (129, 4100, 64)]
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from pydnmfk_b200 import _lib as L
+    from pydnmfk_b200 import device as D
+    L.set_force_generic(False)
+    L.set_tc_min_elems(1)
+    yield D.default_ops()
+    L.set_tc_min_elems(1 << 20)
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _diag(tag, got, ref):
+    bad = np.argwhere(got != ref)
+    rec = dict(tag=tag, shape=list(got.shape), n_bad=int(bad.shape[0]),
+               first_bad=[[int(i), int(j), float(got[i, j]), float(ref[i, j])] for i, j in bad[:12]])
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, 'tc_diag.jsonl'), 'a') as f:
+        f.write(json.dumps(rec) + '\n')
+    return rec
+
+
+def test_tensor_path_is_taken(ops):
+    from pydnmfk_b200 import _lib as L
+    A = torch.rand((1024, 1024), device='cuda')
+    H = torch.rand((32, 1024), device='cuda')
+    ops.ah(A, H)
+    torch.cuda.synchronize()
+    assert L.last_path() == 1, 'tcgen05 path not active (calibration failed or device is not sm_100)'
+    ops.wta(A, torch.rand((1024, 32), device='cuda'))
+    torch.cuda.synchronize()
+    assert L.last_path() == 1
+
+
+@pytest.mark.parametrize('m,n,k', SHAPES)
+def test_exact_on_integer_data(ops, m, n, k):
+    rs = np.random.RandomState(m + n + k)
+    A = rs.randint(0, 8, size=(m, n)).astype(np.float32)
+    H = rs.randint(0, 4, size=(k, n)).astype(np.float32)
+    W = rs.randint(0, 4, size=(m, k)).astype(np.float32)
+    V = ops.ah(_dev(A), _dev(H)).cpu().numpy()
+    Vr = (A.astype(np.int64) @ H.astype(np.int64).T).astype(np.float32)
+    assert np.array_equal(V, Vr), _diag('ah %dx%dx%d' % (m, n, k), V, Vr)
+    Y = ops.wta(_dev(A), _dev(W)).cpu().numpy()
+    Yr = (W.astype(np.int64).T @ A.astype(np.int64)).astype(np.float32)
+    assert np.array_equal(Y, Yr), _diag('wta %dx%dx%d' % (m, n, k), Y, Yr)
+    Yt = ops.wta(_dev(A), _dev(W), transposed_out=True).cpu().numpy()
+    assert np.array_equal(Yt, Yr.T)
+
+
+@pytest.mark.parametrize('m,n,k', SHAPES)
+def test_fp32_accuracy_of_the_split(ops, m, n, k):
+    from pydnmfk_b200 import _lib as L
+    rs = np.random.RandomState(7)
+    A, H, W = rs.rand(m, n).astype(np.float32), rs.rand(k, n).astype(np.float32), rs.rand(m, k).astype(np.float32)
+    f = np.float64
+    V = ops.ah(_dev(A), _dev(H)).cpu().numpy()
+    assert L.last_path() == 1
+    Y = ops.wta(_dev(A), _dev(W)).cpu().numpy()
+    eV, eY = T.rel_fro(V, A.astype(f) @ H.astype(f).T), T.rel_fro(Y, W.astype(f).T @ A.astype(f))
+    L.set_force_generic(True)
+    Vg = ops.ah(_dev(A), _dev(H)).cpu().numpy()
+    Yg = ops.wta(_dev(A), _dev(W)).cpu().numpy()
+    L.set_force_generic(False)
+    gV, gY = T.rel_fro(Vg, A.astype(f) @ H.astype(f).T), T.rel_fro(Yg, W.astype(f).T @ A.astype(f))
+    _diag('acc %dx%dx%d tc(V %.2e Y %.2e) generic(V %.2e Y %.2e)' % (m, n, k, eV, eY, gV, gY), V[:1, :1], V[:1, :1])
+    # fp32-accurate: within a small factor of the plain-fp32 kernels, far below single-pass tf32 (~3e-4)
+    assert eV <= 2e-6 and eY <= 2e-6, (eV, eY, gV, gY)
+
+
+def test_strided_window_and_wide_values(ops):
+    """lda > n (TMA global stride), values spanning many binades."""
+    rs = np.random.RandomState(11)
+    big = (rs.rand(700, 1200) * 2.0 ** rs.randint(-8, 8, size=(700, 1200))).astype(np.float32)
+    Ad = torch.from_numpy(big).cuda()[100:612, 64:1088]        # 512 x 1024 window, ld = 1200, 16-byte aligned
+    A = big[100:612, 64:1088]
+    H, W = rs.rand(32, 1024).astype(np.float32), rs.rand(512, 32).astype(np.float32)
+    f = np.float64
+    assert T.rel_fro(ops.ah(Ad, _dev(H)).cpu().numpy(), A.astype(f) @ H.astype(f).T) <= 2e-6
+    assert T.rel_fro(ops.wta(Ad, _dev(W)).cpu().numpy(), W.astype(f).T @ A.astype(f)) <= 2e-6
+
+
+def test_deterministic(ops):
+    A, H = torch.rand((4096, 4096), device='cuda'), torch.rand((32, 4096), device='cuda')
+    W = torch.rand((4096, 32), device='cuda')
+    assert torch.equal(ops.ah(A, H), ops.ah(A, H)) and torch.equal(ops.wta(A, W), ops.wta(A, W))
