@@ -66,6 +66,8 @@ int dnmf_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int dnmf_set_force_generic(int on);
 /* smallest shard (m*n elements) routed to the tcgen05 path; default 2^20, tests lower it */
 int dnmf_set_tc_min_elems(int64_t elems);
+/* debug/profiling: device buffer of [n_sm][16] uint64 cycle counters filled by the tcgen05 kernels (NULL = off) */
+int dnmf_set_tc_profile(void* device_buf);
 
 int64_t dnmf_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype);
 

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdnmf.so')
+LIB_PATH = os.environ.get('DNMF_LIB_PATH') or os.path.join(_HERE, 'libdnmf.so')   # override: A/B builds only
 
 F32, F64 = 0, 1
 MATH_ACCURATE, MATH_TF32 = 0, 1
@@ -26,6 +26,7 @@ SIGNATURES = {
     'dnmf_device_info': (i32, [C.POINTER(i32)] * 3),
     'dnmf_set_force_generic': (i32, [i32]),
     'dnmf_set_tc_min_elems': (i32, [i64]),
+    'dnmf_set_tc_profile': (i32, [vp]),
     'dnmf_workspace_bytes': (i64, [i32, i64, i64, i64, i32]),
     'dnmf_ah': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, i32, vp, i64, vp]),
     'dnmf_wta': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, i32, i32, vp, i64, vp]),
@@ -58,7 +59,7 @@ SIGNATURES = {
 }
 
 _NO_STATUS = {'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
-              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems'}
+              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile'}
 
 
 class DnmfError(RuntimeError):

@@ -3,19 +3,21 @@
 //   AH  : V[m x k]   = A[m x n] * H[k x n]^T          (dist_nmf.py:198, :730)
 //   WTA : Y^T[n x k] = (W[m x k]^T * A[m x n])^T       (dist_nmf.py:166, :749)
 //
-// Both stream the resident shard A exactly once from HBM with TMA (cp.async.bulk.tensor, 128B swizzle) into a
-// multi-stage shared-memory ring and contract it on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
-// accumulators in TMEM).  fp32 accuracy comes from the 3-term split  A*B ~= Ah*Bh + Ah*Bl + Al*Bh :
-//   - the small operand (H or W) is split once per call into Bcat = [B_hi | B_lo]  (2k "N" rows, K-major),
-//   - the tensor core reads raw fp32 A from shared memory and uses its top 19 bits (= A_hi),
-//   - four "splitter" warps read the tile back from shared memory, compute A_lo = A - A_hi and store it straight
-//     into TENSOR MEMORY (tcgen05.st), so the third term's operand costs no shared-memory bandwidth or capacity,
-//   - per 32-wide K tile the MMA warp issues 4 x { D[:, 0:2k] += Ah[smem] * Bcat^T ;  D[:, k:2k] += Al[tmem] * Bh^T }.
-// The epilogue warps add the two halves of the accumulator and write a per-split partial; the splits are summed
-// in a fixed order by reduce_partials_kernel (deterministic).
+// Both stream the resident shard A exactly once from HBM with TMA (cp.async.bulk.tensor) into a shared-memory ring
+// and contract it on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).  fp32 accuracy
+// comes from the 3-term split  A*B ~= Ah*Bh + Ah*Bl + Al*Bh :
+//   - the small operand (H or W) is split once per call into Bcat = [B_hi | B_lo]  (2k "N" rows, K-major, smem),
+//   - four "splitter" warps pull every A tile from shared memory into registers and store BOTH the raw tile (the
+//     tensor core uses its top 19 bits = A_hi) and A_lo = A - A_hi into TENSOR MEMORY (tcgen05.st): the MMA's A
+//     operand then comes from TMEM, which is what makes a skinny (N = 2k) tf32 MMA cheap -- with A in shared
+//     memory the tensor core is bound by its 32 B/clk A-operand fetch (measured: 128 clk per K=8 step at any N),
+//   - per 32-wide K tile the MMA warp issues 4 x { D[:, 0:2k] += Ah * Bcat^T ;  D[:, k:2k] += Al * Bh^T },
+//   - the tensor core accumulates in fp32 with truncation, so every TC_CHUNK tiles four "drain" warps fold the
+//     TMEM accumulator into fp32 registers (round-to-nearest) and finally write a per-split partial; the splits
+//     are summed in a fixed order by reduce_partials_kernel (deterministic).
 //
-// Warp roles (320 threads, one persistent CTA per SM):  w0 TMA producer | w1 MMA issuer + TMEM owner |
-// w2-5 A_lo splitters | w6-9 drain (TMEM chunk -> fp32 registers -> global partial).
+// Warp roles (one persistent CTA per SM):  w0 A-TMA | w1 MMA issuer + TMEM owner | w2-5 splitters | w6-9 drain |
+// w10 B-TMA | w11-14 second splitter group (k <= 32).
 #include <cuda.h>
 
 #include "generic_passes.cuh"
@@ -26,24 +28,34 @@ namespace {
 
 constexpr int TC_BM = 128;      // outer tile (rows of A for AH, columns of A for WTA) = UMMA M
 constexpr int TC_BK = 32;       // reduced-dimension tile: 32 fp32 = one 128-byte swizzle row = 4 UMMA K steps
-constexpr int TC_THREADS = 320;
-constexpr int TC_CHUNK = 2;      // K-tiles accumulated in TMEM before the drain warps fold them into registers
+constexpr int TC_THREADS_BASE = 352;  // 11 warps: A producer | MMA | 4 splitters | 4 drain | B producer (+4 splitters)
+constexpr int TC_CHUNK = 4;      // K-tiles accumulated in TMEM before the drain warps fold them into registers
 
-// Shared memory per stage: the raw A tile (16 KB) + the Bcat tile.  TMEM (512 columns): NBUF accumulator buffers of
-// 2K columns, then one 32-column A_lo slot per stage (the A_lo operand of the third term never touches smem).
+// Three decoupled rings:
+//   A ring   (shared memory, SA slots x 16 KB): TMA -> splitter warps; freed as soon as the tile is in registers
+//   B ring   (shared memory, SB slots x 2K*128 B): TMA -> tensor core (B operand); freed by tcgen05.commit
+//   operand ring (TENSOR memory, NT slots x 64 columns): raw A (= A_hi for the tensor core) and A_lo, written by the
+//            splitters with tcgen05.st, read by tcgen05.mma as the A operand; freed by tcgen05.commit
+// plus NBUF accumulator buffers of 2K TMEM columns.  The tensor core therefore reads only B from shared memory.
 template <int K>
 struct TcCfg {
   static constexpr int N2 = 2 * K;
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
   static constexpr int B_BYTES = N2 * TC_BK * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (K == 16) ? 10 : (K == 32) ? 9 : 6;
+  static constexpr int SA = (K == 16) ? 10 : (K == 32) ? 8 : 7;
+  static constexpr int SB = (K == 16) ? 12 : (K == 32) ? 10 : 6;
   static constexpr int NBUF = (K == 16) ? 4 : (K == 32) ? 3 : 2;
-  static constexpr int ALO_COL0 = NBUF * N2;
+  // splitter groups working on alternate tiles (hides the tcgen05.st round trip); the K=64 drain warps need too many
+  // registers for 480 threads per CTA, so that variant keeps one group
+  static constexpr int SG = (K <= 32) ? 2 : 1;
+  static constexpr int THREADS = TC_THREADS_BASE + 128 * (SG - 1);
+  static constexpr int OP_COL0 = NBUF * N2;
+  static constexpr int NT = (512 - OP_COL0) / 64;
   static constexpr int TMEM_COLS = 512;
-  static_assert(ALO_COL0 + STAGES * TC_BK <= 512, "TMEM has 512 columns");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int SMEM_BYTES = SA * A_BYTES + SB * B_BYTES + 1024 + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory limit");
+  static_assert((2 * SA + 2 * SB + 2 * NT + 2 * NBUF + 1) * 8 <= BAR_BYTES, "barrier area too small");
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -104,18 +116,75 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// same with the A operand in tensor memory (lane = row, one 32-bit column per K element)
+// A operand in tensor memory (lane = row, one 32-bit column per K element).  MUST be executed by a fully converged
+// warp: the elect.sync predicate inside the asm block picks the issuing lane.  Issuing from a divergent
+// `if (lane == 0)` region makes ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY loop that costs ~60-100 cycles
+// per MMA (measured, tools/umma_bench.cu) -- more than a skinny N <= 64 MMA itself (N/2 cycles).
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // mbarrier arrives once every tcgen05 op issued so far by this thread has completed
+// (converged warp, elected lane -- see umma_tf32_ts)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar) : "memory");
+}
+
+// One K tile (4 K=8 steps) of the 3-term split, plus the tcgen05.commits that release the operand slot, the B slot
+// and (at a chunk end) the accumulator, issued from ONE asm block under a single elect.sync: the uniform-datapath
+// set-up (ELECT, R2UR of every operand) is paid once per tile instead of once per instruction.
+//   D[:, 0:2K] (+)= A_raw[tmem] * Bcat^T        (N = 2K)      D[:, K:2K] += A_lo[tmem] * B_hi^T     (N = K)
+template <int K>
+__device__ __forceinline__ void umma_tile_ts(uint32_t d_tmem, uint32_t a_raw, uint64_t bdesc, uint32_t acc_first,
+                                             uint32_t idesc_full, uint32_t idesc_half, uint32_t bar_t, uint32_t bar_b,
+                                             uint32_t bar_acc, uint32_t chunk_end, uint32_t skip_lo) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q, p0, p1, pc, pl;\n\t"
+      ".reg .b32 dl, a1, a2, a3, l0, l1, l2, l3;\n\t"
+      ".reg .b64 b1, b2, b3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p0, %3, 0;\n\t"
+      "setp.eq.b32 p1, 0, 0;\n\t"
+      "setp.ne.b32 pc, %9, 0;\n\t"
+      "and.pred pc, pc, q;\n\t"
+      "setp.eq.b32 pl, %10, 0;\n\t"
+      "and.pred pl, pl, q;\n\t"
+      "add.u32 dl, %0, %11;\n\t"
+      "add.u32 l0, %1, 32;\n\t"
+      "add.u32 a1, %1, 8;\n\t"
+      "add.u32 l1, %1, 40;\n\t"
+      "add.u32 a2, %1, 16;\n\t"
+      "add.u32 l2, %1, 48;\n\t"
+      "add.u32 a3, %1, 24;\n\t"
+      "add.u32 l3, %1, 56;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "add.u64 b2, %2, 4;\n\t"
+      "add.u64 b3, %2, 6;\n\t"
+      "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %4, p0;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l0], %2, %5, p1;\n\t"
+      "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [a1], b1, %4, p1;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l1], b1, %5, p1;\n\t"
+      "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], b2, %4, p1;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l2], b2, %5, p1;\n\t"
+      "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], b3, %4, p1;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l3], b3, %5, p1;\n\t"
+      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+      "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "}\n"
+      ::"r"(d_tmem), "r"(a_raw), "l"(bdesc), "r"(acc_first), "r"(idesc_full), "r"(idesc_half), "r"(bar_t), "r"(bar_b),
+        "r"(bar_acc), "r"(chunk_end), "r"(skip_lo), "n"(K)
+      : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -175,38 +244,45 @@ __device__ __forceinline__ float tf32_round_up(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// cycle accounting for DNMF_TC_DBG & 16 (per-role time split written to a debug buffer; off in production)
+#define TC_T(var) do { if (prof) { const long long _n = clock64(); var += _n - tprev; tprev = _n; } } while (0)
+
 // ---------------------------------------------------------------------------------------------------------
 // persistent tcgen05 kernel
-//   MODE 0 (AH):  X = rows of A (m), reduced = columns (n);  A tile = one TMA box {32 cols, 128 rows}, K-major
-//   MODE 1 (WTA): X = columns of A (n), reduced = rows (m);  A tile = four TMA boxes {32 cols, 32 rows}, MN-major,
-//                 written with the 128B/32B-atom swizzle (the MN-major layout tf32 operands require)
-//   B tile = one TMA box {32, 2K} of Bcat[2K][reduced], K-major.
+//   MODE 0 (AH):  X = rows of A (m), reduced = columns (n);  A tile = TMA box {32 cols, 128 rows}, 128B swizzle
+//                 (so that a thread can read "its" row with conflict-free 128-bit loads)
+//   MODE 1 (WTA): X = columns of A (n), reduced = rows (m);  A tile = TMA box {128 cols, 32 rows}, no swizzle
+//                 (a thread reads "its" column, one coalesced 32-bit load per K row)
+//   B tile = TMA box {32, 2K} of Bcat[2K][reduced], K-major, 128B swizzle (UMMA B operand).
 //   Output: P[split][x][K] (ld = K), x < x_len.
 // ---------------------------------------------------------------------------------------------------------
 template <int K, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<K>::THREADS, 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                float* __restrict__ P, int64_t split_stride, int64_t x_len, int x_blocks, int kt_total,
-               int kt_per_split, int num_units, int hi_mode, int dbg) {
+               int kt_per_split, int num_units, int hi_mode, int dbg, unsigned long long* __restrict__ prof) {
   using Cfg = TcCfg<K>;
-  // dbg (DNMF_TC_DBG, timing experiments only, results become wrong): 1 = splitter skips its work, 2 = no chunked
-  // drain, 4 = skip the A_lo MMA, 8 = skip the main MMA
-  const int chunk = (dbg & 2) ? (1 << 30) : TC_CHUNK;
-  constexpr int STAGES = Cfg::STAGES;
-  constexpr int N2 = Cfg::N2;
-  constexpr int NBUF = Cfg::NBUF;
+  constexpr int SA = Cfg::SA, SB = Cfg::SB, NT = Cfg::NT, NBUF = Cfg::NBUF, N2 = Cfg::N2;
+  // dbg (DNMF_TC_DBG, timing experiments only, results become wrong): 1 = splitter skips its work, 4 = skip the
+  // A_lo MMAs
+  constexpr int chunk = TC_CHUNK;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  // per stage: [A 16K][Bcat]
-  const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto split_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto accf_bar = [&](int b) { return bars + 8u * (3 * STAGES + b); };
-  auto acce_bar = [&](int b) { return bars + 8u * (3 * STAGES + NBUF + b); };
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 2 * NBUF);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 2 * NBUF));
+  const uint32_t sA0 = base, sB0 = base + SA * Cfg::A_BYTES;
+  const uint32_t bars = sB0 + SB * Cfg::B_BYTES;
+  auto a_full = [&](int s) { return bars + 8u * s; };
+  auto a_free = [&](int s) { return bars + 8u * (SA + s); };
+  auto b_full = [&](int s) { return bars + 8u * (2 * SA + s); };
+  auto b_free = [&](int s) { return bars + 8u * (2 * SA + SB + s); };
+  auto t_full = [&](int s) { return bars + 8u * (2 * SA + 2 * SB + s); };
+  auto t_free = [&](int s) { return bars + 8u * (2 * SA + 2 * SB + NT + s); };
+  auto accf_bar = [&](int b) { return bars + 8u * (2 * SA + 2 * SB + 2 * NT + b); };
+  auto acce_bar = [&](int b) { return bars + 8u * (2 * SA + 2 * SB + 2 * NT + NBUF + b); };
+  constexpr int SLOT_IDX = 2 * SA + 2 * SB + 2 * NT + 2 * NBUF;
+  const uint32_t tmem_slot = bars + 8u * SLOT_IDX;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + SA * Cfg::A_BYTES + SB * Cfg::B_BYTES + 8 * SLOT_IDX);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -214,15 +290,10 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(split_bar(s), 4);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int b = 0; b < NBUF; ++b) {
-      mbar_init(accf_bar(b), 1);
-      mbar_init(acce_bar(b), 4);
-    }
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_free(s), 4); }
+    for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_free(s), 1); }
+    for (int s = 0; s < NT; ++s) { mbar_init(t_full(s), 4); mbar_init(t_free(s), 1); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -232,40 +303,53 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== A producer (TMA) =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      long long tprev = clock64(), t_wait = 0, t_issue = 0, t0 = tprev;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int xb = unit % x_blocks, sp = unit / x_blocks;
         const int kt0 = sp * kt_per_split;
         const int kt1 = min(kt_total, kt0 + kt_per_split);
         for (int kt = kt0; kt < kt1; ++kt) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sA = base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + Cfg::A_BYTES;
-          mbar_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
-          if (MODE == 0) {
-            tma_load_2d(sA, &tmA, full_bar(stage), kt * TC_BK, xb * TC_BM);
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              tma_load_2d(sA + g * 4096, &tmA, full_bar(stage), xb * TC_BM + g * 32, kt * TC_BK);
-          }
-          tma_load_2d(sB, &tmB, full_bar(stage), kt * TC_BK, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          mbar_wait(a_free(s), ph ^ 1u);
+          TC_T(t_wait);
+          mbar_expect_tx(a_full(s), Cfg::A_BYTES);
+          if (MODE == 0) tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, a_full(s), kt * TC_BK, xb * TC_BM);
+          else tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, a_full(s), xb * TC_BM, kt * TC_BK);
+          if (++s == SA) { s = 0; ph ^= 1u; }
+          TC_T(t_issue);
+        }
+      }
+      if (prof) { prof[blockIdx.x * 16 + 0] = t_wait; prof[blockIdx.x * 16 + 1] = t_issue; prof[blockIdx.x * 16 + 15] = clock64() - t0; }
+    }
+  } else if (warp == 10) {
+    // ===================== B producer (TMA) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int sp = unit / x_blocks;
+        const int kt0 = sp * kt_per_split;
+        const int kt1 = min(kt_total, kt0 + kt_per_split);
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(b_free(s), ph ^ 1u);
+          mbar_expect_tx(b_full(s), Cfg::B_BYTES);
+          tma_load_2d(sB0 + s * Cfg::B_BYTES, &tmB, b_full(s), kt * TC_BK, 0);
+          if (++s == SB) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_full = make_idesc(N2, MODE);
-      constexpr uint32_t idesc_half = make_idesc(K, 0);     // A_lo comes from TMEM: always [M][K]
-      int stage = 0;
-      uint32_t phase = 0;
-      int buf = 0;
-      uint32_t accphase = 0;
+    // ===================== MMA issuer (both A operands come from tensor memory) =====================
+    // the whole warp runs this loop converged; one elected lane issues each tcgen05 instruction
+    {
+      constexpr uint32_t idesc_full = make_idesc(N2, 0);
+      constexpr uint32_t idesc_half = make_idesc(K, 0);
+      int sb = 0, ts = 0, buf = 0;
+      uint32_t pb = 0, pt = 0, accphase = 0;
+      long long tprev = clock64(), t_acce = 0, t_tfull = 0, t_bfull = 0, t_mma = 0, t_commit = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int sp = unit / x_blocks;
         const int kt0 = sp * kt_per_split;
@@ -274,87 +358,104 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int in_chunk = (kt - kt0) % chunk;
           if (in_chunk == 0) {                      // new accumulation chunk: wait for the drain warps
             mbar_wait(acce_bar(buf), accphase ^ 1u);
-            tc_fence_after();
           }
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N2);
-          mbar_wait(split_bar(stage), phase);
+          TC_T(t_acce);
+          mbar_wait(t_full(ts), pt);
+          TC_T(t_tfull);
+          mbar_wait(b_full(sb), pb);
+          TC_T(t_bfull);
           tc_fence_after();
-          const uint32_t sA = base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + Cfg::A_BYTES;
-          const uint32_t a_lo_tmem = tmem_base + (uint32_t)(Cfg::ALO_COL0 + stage * TC_BK);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint64_t a_hi;
-            if (MODE == 0)     // K-major: 8-row groups 1024 B apart, K step = 32 B inside the swizzled row
-              a_hi = make_smem_desc(sA + kk * 32, 16, 1024);
-            else               // MN-major (SWIZZLE_128B_BASE32B): 32-column groups 4096 B apart (LBO), 4-row K groups
-                               // 512 B apart (SBO); one K=8 step = 8 rows = 1024 B
-              a_hi = make_smem_desc(sA + kk * 1024, 4096, 512, 1);
-            const uint64_t b = make_smem_desc(sB + kk * 32, 16, 1024);
-            // cols [0,K): Ah*Bh (large term, alone in its accumulator);  cols [K,2K): Ah*Bl + Al*Bh (small terms)
-            if (!(dbg & 8)) umma_tf32(d_tmem, a_hi, b, idesc_full, (in_chunk > 0 || kk > 0) ? 1u : 0u);
-            if (!(dbg & 4)) umma_tf32_ts(d_tmem + K, a_lo_tmem + kk * 8, b, idesc_half, 1u);
-          }
-          umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          if (in_chunk == chunk - 1 || kt == kt1 - 1) {
-            umma_commit(accf_bar(buf));           // chunk complete -> drain warps
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N2);
+          const uint32_t a_raw = tmem_base + (uint32_t)(Cfg::OP_COL0 + ts * 64);
+          const uint32_t sB = sB0 + sb * Cfg::B_BYTES;
+          const bool chunk_end = (in_chunk == chunk - 1) || (kt == kt1 - 1);
+          // cols [0,K): Ah*Bh (large term, alone in its accumulator);  cols [K,2K): Ah*Bl + Al*Bh (small terms)
+          umma_tile_ts<K>(d_tmem, a_raw, make_smem_desc(sB, 16, 1024), in_chunk > 0 ? 1u : 0u, idesc_full, idesc_half,
+                          t_free(ts), b_free(sb), accf_bar(buf), chunk_end ? 1u : 0u, (dbg & 4) ? 1u : 0u);
+          TC_T(t_mma);
+          if (++ts == NT) { ts = 0; pt ^= 1u; }
+          if (++sb == SB) { sb = 0; pb ^= 1u; }
+          if (chunk_end) {
             if (++buf == NBUF) { buf = 0; accphase ^= 1u; }
           }
+          TC_T(t_commit);
+          __syncwarp();
         }
       }
+      if (prof && lane == 0) {
+        prof[blockIdx.x * 16 + 2] = t_acce; prof[blockIdx.x * 16 + 3] = t_tfull; prof[blockIdx.x * 16 + 4] = t_bfull;
+        prof[blockIdx.x * 16 + 5] = t_mma; prof[blockIdx.x * 16 + 6] = t_commit;
+      }
     }
-  } else if (warp < 6) {
-    // ===================== A_lo splitters (warps 2-5): smem A tile -> A - hi(A) -> TMEM =====================
-    // Thread (q, lane) owns accumulator row q*32+lane (a row of A for AH, a column of A for WTA) and writes its 32
-    // K-values of the tile into the stage's A_lo slot in tensor memory.
+  } else if (warp < 6 || warp >= 11) {
+    // ===================== splitters (warps 2-5 [+ 11-14]): smem A tile -> registers -> {A, A - hi(A)} in TMEM =====
+    // Thread (q, lane) owns accumulator row q*32+lane: a row of A (AH) or a column of A (WTA).  With two groups,
+    // group g takes the tiles whose running index is congruent to g (mod 2).
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    int stage = 0;
-    uint32_t phase = 0;
+    const int group = (warp >= 11) ? 1 : 0;
+    int tile = 0;
+    long long tprev = clock64(), t_afull = 0, t_load = 0, t_tfree = 0, t_store = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int sp = unit / x_blocks;
       const int kt0 = sp * kt_per_split;
       const int kt1 = min(kt_total, kt0 + kt_per_split);
-      for (int kt = kt0; kt < kt1; ++kt) {
-        mbar_wait(full_bar(stage), phase);
-        const uint8_t* tile = base_ptr + stage * Cfg::STAGE_BYTES;
-        uint32_t lo[32];
+      for (int kt = kt0; kt < kt1; ++kt, ++tile) {
+        if (Cfg::SG > 1 && (tile & 1) != group) continue;
+        const int sa = tile % SA, ts = tile % NT;
+        const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u;
+        mbar_wait(a_full(sa), pa);
+        TC_T(t_afull);
+        const uint8_t* tile = base_ptr + sa * Cfg::A_BYTES;
+        uint32_t raw[32], lo[32];
         if (dbg & 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) lo[j] = 0;
+          for (int j = 0; j < 32; ++j) raw[j] = 0;
         } else if (MODE == 0) {
           // row r = 128 contiguous bytes, 16-byte chunk c stored at position c ^ (r & 7)  (SWIZZLE_128B)
           const uint8_t* row = tile + r * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
-            lo[4 * c + 0] = __float_as_uint(tf32_round_up(v.x - tf32_hi(v.x, hi_mode)));
-            lo[4 * c + 1] = __float_as_uint(tf32_round_up(v.y - tf32_hi(v.y, hi_mode)));
-            lo[4 * c + 2] = __float_as_uint(tf32_round_up(v.z - tf32_hi(v.z, hi_mode)));
-            lo[4 * c + 3] = __float_as_uint(tf32_round_up(v.w - tf32_hi(v.w, hi_mode)));
+            const uint4 v = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+            raw[4 * c + 0] = v.x; raw[4 * c + 1] = v.y; raw[4 * c + 2] = v.z; raw[4 * c + 3] = v.w;
           }
         } else {
-          // box q holds columns q*32..q*32+31: K-row j at j*128 bytes, 32-byte chunk (lane>>3) stored at position
-          // (lane>>3) ^ (j & 3)  (SWIZZLE_128B_ATOM_32B)
-          const uint8_t* box = tile + q * 4096 + (lane & 7) * 4;
+          // [32 K rows][128 columns] row-major: one coalesced 32-bit load per K row
+          const uint8_t* col = tile + r * 4;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = *reinterpret_cast<const float*>(box + j * 128 + ((((lane >> 3) ^ (j & 3))) << 5));
-            lo[j] = __float_as_uint(tf32_round_up(v - tf32_hi(v, hi_mode)));
-          }
+          for (int j = 0; j < 32; ++j) raw[j] = *reinterpret_cast<const uint32_t*>(col + j * 512);
         }
         // a - hi(a) is exact; rounding it to tf32 here (nearest) instead of letting the tensor core truncate it
         // removes the one-sided error of the third term
-        if (!(dbg & 1)) {
-          tmem_st_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ALO_COL0 + stage * TC_BK), lo);
-          tmem_st_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(raw[j]);
+          lo[j] = __float_as_uint(tf32_round_up(v - tf32_hi(v, hi_mode)));
         }
+        TC_T(t_load);
+        mbar_wait(t_free(ts), pt ^ 1u);
+        TC_T(t_tfree);
+        tc_fence_after();
+        if (!(dbg & 1)) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::OP_COL0 + ts * 64);
+          tmem_st_x32(taddr, raw);
+          tmem_st_x32(taddr + 32, lo);
+        }
+        // Release the smem slot only now: the tcgen05.st instructions above consume every loaded register, so all
+        // shared-memory loads of this tile have completed (an arrive placed right after the loads could overtake
+        // loads still in flight and let TMA overwrite the tile under them).
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_free(sa));
+        if (!(dbg & 1)) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(split_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (lane == 0) mbar_arrive(t_full(ts));
+        TC_T(t_store);
       }
+    }
+    if (prof && warp == 2 && lane == 0) {
+      prof[blockIdx.x * 16 + 7] = t_afull; prof[blockIdx.x * 16 + 8] = t_load; prof[blockIdx.x * 16 + 9] = t_tfree;
+      prof[blockIdx.x * 16 + 10] = t_store;
     }
   } else {
     // ===================== drain warps 6-9: TMEM chunk -> fp32 register accumulators -> global partial ==========
@@ -364,16 +465,18 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int buf = 0;
     uint32_t accphase = 0;
     constexpr int CH = 16;
+    long long tprev = clock64(), t_accf = 0, t_drain = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int xb = unit % x_blocks, sp = unit / x_blocks;
       const int kt0 = sp * kt_per_split;
       const int kt1 = min(kt_total, kt0 + kt_per_split);
-      const int nchunks = (dbg & 2) ? 1 : (kt1 - kt0 + TC_CHUNK - 1) / TC_CHUNK;
+      const int nchunks = (kt1 - kt0 + TC_CHUNK - 1) / TC_CHUNK;
       float acc[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) acc[j] = 0.f;
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(accf_bar(buf), accphase);
+        TC_T(t_accf);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N2);
         constexpr int HALF = (K >= 32) ? 32 : K;       // columns folded per batch of loads
@@ -393,6 +496,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(acce_bar(buf));   // TMEM buffer may be overwritten
         if (++buf == NBUF) { buf = 0; accphase ^= 1u; }
+        TC_T(t_drain);
       }
       const int64_t x = (int64_t)xb * TC_BM + q * 32 + lane;
       if (x < x_len) {
@@ -402,6 +506,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           *reinterpret_cast<float4*>(orow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
     }
+    if (prof && warp == 6 && lane == 0) { prof[blockIdx.x * 16 + 11] = t_accf; prof[blockIdx.x * 16 + 12] = t_drain; }
   }
 
   tc_fence_before();
@@ -515,6 +620,7 @@ TcPlan tc_plan(int64_t x_len, int64_t r_len, int k) {
   return p;
 }
 
+unsigned long long* g_prof = nullptr;   // debug: per-CTA role timings (dnmf_set_tc_profile)
 int g_hi_mode = -1;     // -1 unknown, 0 truncate, 1 round-to-nearest-even, 2 = tensor path unusable
 int64_t g_min_elems = -1;
 
@@ -524,9 +630,9 @@ int launch_pass(const CUtensorMap& tmA, const CUtensorMap& tmB, float* P, int64_
   auto kern = tc_pass_kernel<K, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<K>::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_fail(e, "tc_pass_kernel smem attribute");
-  kern<<<pl.grid, TC_THREADS, TcCfg<K>::SMEM_BYTES, st>>>(tmA, tmB, P, split_stride, x_len, pl.x_blocks, pl.kt_total,
+  kern<<<pl.grid, TcCfg<K>::THREADS, TcCfg<K>::SMEM_BYTES, st>>>(tmA, tmB, P, split_stride, x_len, pl.x_blocks, pl.kt_total,
                                                             pl.kt_per_split, pl.num_units, hi_mode,
-                                                            getenv("DNMF_TC_DBG") ? atoi(getenv("DNMF_TC_DBG")) : 0);
+                                                            getenv("DNMF_TC_DBG") ? atoi(getenv("DNMF_TC_DBG")) : 0, g_prof);
   DNMF_LAUNCH_CHECK("tc_pass_kernel");
   return 0;
 }
@@ -564,7 +670,7 @@ int tc_run(int mode, const float* A, int64_t lda, const float* B, int64_t ldbsrc
   alignas(64) CUtensorMap tmA, tmB;
   int rc;
   if (mode == 0) rc = make_map(&tmA, A, m, n, lda, TC_BK, TC_BM);
-  else rc = make_map(&tmA, A, m, n, lda, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  else rc = make_map(&tmA, A, m, n, lda, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   rc = make_map(&tmB, Bcat, 2 * k, r_len, pl.ldb, TC_BK, 2 * k);
   if (rc) return rc;
@@ -657,6 +763,8 @@ bool tc_eligible(int op, const void* A, int64_t lda, int64_t m, int64_t n, int64
   calibrate();
   return g_hi_mode == 0 || g_hi_mode == 1;
 }
+
+void tc_set_profile(void* buf) { g_prof = reinterpret_cast<unsigned long long*>(buf); }
 
 void tc_set_min_elems(int64_t elems) { g_min_elems = elems < 0 ? 0 : elems; }
 

@@ -62,10 +62,10 @@ def _compare(case, res):
         dW, dH = T.rel_fro(o['W'], g['W']), T.rel_fro(o['H'], g['H'])
         assert dW <= tf and dH <= tf, '%s rank %d: rel diff W %.3g H %.3g (tol %.1g)' % (case['name'], r, dW, dH, tf)
         ge = float(g['err'])
-        if case['data'] == 'lowrank':
-            assert o['err'] < 1e-3      # the reference's own assertion (tests/test_dist_nmf_1d.py:46)
-        else:
-            assert abs(o['err'] - ge) <= te * abs(ge), '%s rank %d: err %.9g vs %.9g' % (case['name'], r, o['err'], ge)
+        # (absolute slack: on exact low-rank data the error converges towards 0 and only its magnitude is meaningful)
+        slack = 1e-6 if case['dtype'] == 'float32' else 1e-9
+        assert abs(o['err'] - ge) <= te * abs(ge) + (slack if case['data'] == 'lowrank' else 0.0), \
+            '%s rank %d: err %.9g vs %.9g' % (case['name'], r, o['err'], ge)
 
 
 def _run(case, force_generic=False):

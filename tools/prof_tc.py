@@ -17,8 +17,24 @@ ap.add_argument('--n', type=int, default=32768)
 ap.add_argument('--k', type=int, default=32)
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--kl', action='store_true')
+ap.add_argument('--roles', action='store_true', help='print the per-warp-role cycle split of the tcgen05 kernel')
 a = ap.parse_args()
 ops = D.default_ops()
+
+
+def copy_peak():
+    """STREAM-style copy on this box (what MEASURED_PEAKS.json's hbm_gbs is): read + write bytes / time, best of 5."""
+    x = torch.empty(1 << 30, dtype=torch.bfloat16, device='cuda')
+    y = torch.empty_like(x)
+    best = 1e9
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); y.copy_(x); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2 * x.numel() * 2 / best / 1e6
+
+
+print('copy peak on this box: %.0f GB/s' % copy_peak(), flush=True)
 A = torch.rand((a.m, a.n), device='cuda')
 H = torch.rand((a.k, a.n), device='cuda')
 W = torch.rand((a.m, a.k), device='cuda')
@@ -34,3 +50,20 @@ for _ in range(a.reps):
     if a.kl:
         msg += '  kl_uht %.3f ms  kl_wtu %.3f ms' % (e[2].elapsed_time(e[3]), e[3].elapsed_time(e[4]))
     print(msg, flush=True)
+
+if a.roles:
+    from pydnmfk_b200 import _lib as L
+    names = ['A-prod wait a_free', 'A-prod issue', 'MMA wait acce', 'MMA wait t_full', 'MMA wait b_full', 'MMA issue', 'MMA commit',
+             'split wait a_full', 'split load+math', 'split wait t_free', 'split store', 'drain wait accf', 'drain work', '', '', 'total']
+    for nm, fn in (('ah', lambda: ops.ah(A, H)), ('wta', lambda: ops.wta(A, W))):
+        buf = torch.zeros(148 * 16, dtype=torch.int64, device='cuda')
+        L.call('dnmf_set_tc_profile', buf.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        L.call('dnmf_set_tc_profile', None)
+        v = buf.cpu().numpy().reshape(148, 16).astype(float)
+        tot = v[:, 15].mean()
+        print(nm, 'cycles per CTA %.0f' % tot)
+        for i, n in enumerate(names):
+            if n and i != 15:
+                print('   %-22s %5.1f%%' % (n, 100 * v[:, i].mean() / tot))
