@@ -247,7 +247,7 @@ static int sum_rows_of(const void* X, int64_t ldx, int64_t rows, int64_t cols, v
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)sp.chunks);
   DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)X, ldx, rows, cols, sp.per_chunk, (double*)ws, sq)));
   DNMF_LAUNCH_CHECK("colsum_partial_kernel");
-  const unsigned g2 = (unsigned)ceil_div(cols, 256);
+  const unsigned g2 = (unsigned)ceil_div(cols * 32, 256);
   if (out_f64) sum_partials_kernel<double><<<g2, 256, 0, st>>>((const double*)ws, (int)sp.chunks, cols, (double*)out);
   else if (dtype == DNMF_F32) sum_partials_kernel<float><<<g2, 256, 0, st>>>((const double*)ws, (int)sp.chunks, cols, (float*)out);
   else sum_partials_kernel<double><<<g2, 256, 0, st>>>((const double*)ws, (int)sp.chunks, cols, (double*)out);
@@ -275,7 +275,7 @@ int dnmf_rowsum(const void* X, int64_t ldx, int64_t rows, int64_t cols, void* ou
   dim3 grid((unsigned)rows, (unsigned)sp.chunks);
   DISPATCH_T(dtype, (rowsum_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)X, ldx, rows, cols, sp.per_chunk, (double*)ws, 0)));
   DNMF_LAUNCH_CHECK("rowsum_partial_kernel");
-  const unsigned g2 = (unsigned)ceil_div(rows, 256);
+  const unsigned g2 = (unsigned)ceil_div(rows * 32, 256);
   if (dtype == DNMF_F32) sum_partials_kernel<float><<<g2, 256, 0, st>>>((const double*)ws, (int)sp.chunks, rows, (float*)out);
   else sum_partials_kernel<double><<<g2, 256, 0, st>>>((const double*)ws, (int)sp.chunks, rows, (double*)out);
   DNMF_LAUNCH_CHECK("sum_partials_kernel");

@@ -55,14 +55,18 @@ gram_partial_kernel(const T* __restrict__ X, int64_t ldx, int64_t rows, int k, i
   }
 }
 
+// one warp per output element: lanes stride over the block partials, then a fixed-order shuffle tree (deterministic)
 template <typename T>
-__global__ void gram_reduce_kernel(const T* __restrict__ P, int nblocks, int KP, int k, T* __restrict__ G) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const T* __restrict__ P, int nblocks, int KP, int k, T* __restrict__ G) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (e >= k * k) return;
   const int i = e / k, j = e % k;
   T acc = T(0);
-  for (int b = 0; b < nblocks; ++b) acc += P[(int64_t)b * KP * KP + i * KP + j];
-  G[e] = acc;
+  for (int b = lane; b < nblocks; b += 32) acc += P[(int64_t)b * KP * KP + i * KP + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) G[e] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -240,14 +244,16 @@ colsum_partial_kernel(const T* __restrict__ X, int64_t ldx, int64_t rows, int64_
   }
 }
 
-// out[c] = (T) sum_chunks P[chunk][c]
+// out[c] = (T) sum_chunks P[chunk][c]; one warp per output, fixed-order shuffle tree
 template <typename TO>
-__global__ void sum_partials_kernel(const double* __restrict__ P, int nparts, int64_t count, TO* __restrict__ out) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restrict__ P, int nparts, int64_t count, TO* __restrict__ out) {
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (idx >= count) return;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += P[(int64_t)p * count + idx];
-  out[idx] = (TO)s;
+  for (int p = lane; p < nparts; p += 32) s += P[(int64_t)p * count + idx];
+  s = warp_sum(s);
+  if (lane == 0) out[idx] = (TO)s;
 }
 
 // rowsum partial: grid (rows, nchunks), block 256: P[chunk][row]   (sq: sum of squares)

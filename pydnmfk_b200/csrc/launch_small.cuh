@@ -67,7 +67,7 @@ int gram_dispatch(const T* X, int64_t ldx, int64_t rows, int k, int trans, T* G,
     if (trans) gram_partial_kernel<T, KP, true><<<(unsigned)g.blocks, kGramThreads, 0, st>>>(X, ldx, rows, k, g.rows_per_block, ws);
     else gram_partial_kernel<T, KP, false><<<(unsigned)g.blocks, kGramThreads, 0, st>>>(X, ldx, rows, k, g.rows_per_block, ws);
     DNMF_LAUNCH_CHECK("gram_partial_kernel");
-    gram_reduce_kernel<T><<<(unsigned)ceil_div((int64_t)k * k, 256), 256, 0, st>>>(ws, (int)g.blocks, KP, k, G);
+    gram_reduce_kernel<T><<<(unsigned)ceil_div((int64_t)k * k * 32, 256), 256, 0, st>>>(ws, (int)g.blocks, KP, k, G);
     DNMF_LAUNCH_CHECK("gram_reduce_kernel");
   });
   return 0;
