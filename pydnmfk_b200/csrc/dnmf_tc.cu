@@ -18,16 +18,13 @@
 //
 // Warp roles (one persistent CTA per SM):  w0 A-TMA | w1 MMA issuer + TMEM owner | w2-5 splitters | w6-9 drain |
 // w10 B-TMA | w11-14 second splitter group (k <= 32).
-#include <cuda.h>
-
 #include "generic_passes.cuh"
 #include "tc_api.cuh"
+#include "tc_common.cuh"
 
 namespace dnmf {
 namespace {
 
-constexpr int TC_BM = 128;      // outer tile (rows of A for AH, columns of A for WTA) = UMMA M
-constexpr int TC_BK = 32;       // reduced-dimension tile: 32 fp32 = one 128-byte swizzle row = 4 UMMA K steps
 constexpr int TC_THREADS_BASE = 352;  // 11 warps: A producer | MMA | 4 splitters | 4 drain | B producer (+4 splitters)
 constexpr int TC_CHUNK = 4;      // K-tiles accumulated in TMEM before the drain warps fold them into registers
 
@@ -57,195 +54,6 @@ struct TcCfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory limit");
   static_assert((2 * SA + 2 * SB + 2 * NT + 2 * NBUF + 1) * 8 <= BAR_BYTES, "barrier area too small");
 };
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// A operand in tensor memory (lane = row, one 32-bit column per K element).  MUST be executed by a fully converged
-// warp: the elect.sync predicate inside the asm block picks the issuing lane.  Issuing from a divergent
-// `if (lane == 0)` region makes ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY loop that costs ~60-100 cycles
-// per MMA (measured, tools/umma_bench.cu) -- more than a skinny N <= 64 MMA itself (N/2 cycles).
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives once every tcgen05 op issued so far by this thread has completed
-// (converged warp, elected lane -- see umma_tf32_ts)
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(bar) : "memory");
-}
-
-// One K tile (4 K=8 steps) of the 3-term split, plus the tcgen05.commits that release the operand slot, the B slot
-// and (at a chunk end) the accumulator, issued from ONE asm block under a single elect.sync: the uniform-datapath
-// set-up (ELECT, R2UR of every operand) is paid once per tile instead of once per instruction.
-//   D[:, 0:2K] (+)= A_raw[tmem] * Bcat^T        (N = 2K)      D[:, K:2K] += A_lo[tmem] * B_hi^T     (N = K)
-template <int K>
-__device__ __forceinline__ void umma_tile_ts(uint32_t d_tmem, uint32_t a_raw, uint64_t bdesc, uint32_t acc_first,
-                                             uint32_t idesc_full, uint32_t idesc_half, uint32_t bar_t, uint32_t bar_b,
-                                             uint32_t bar_acc, uint32_t chunk_end, uint32_t skip_lo) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q, p0, p1, pc, pl;\n\t"
-      ".reg .b32 dl, a1, a2, a3, l0, l1, l2, l3;\n\t"
-      ".reg .b64 b1, b2, b3;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.ne.b32 p0, %3, 0;\n\t"
-      "setp.eq.b32 p1, 0, 0;\n\t"
-      "setp.ne.b32 pc, %9, 0;\n\t"
-      "and.pred pc, pc, q;\n\t"
-      "setp.eq.b32 pl, %10, 0;\n\t"
-      "and.pred pl, pl, q;\n\t"
-      "add.u32 dl, %0, %11;\n\t"
-      "add.u32 l0, %1, 32;\n\t"
-      "add.u32 a1, %1, 8;\n\t"
-      "add.u32 l1, %1, 40;\n\t"
-      "add.u32 a2, %1, 16;\n\t"
-      "add.u32 l2, %1, 48;\n\t"
-      "add.u32 a3, %1, 24;\n\t"
-      "add.u32 l3, %1, 56;\n\t"
-      "add.u64 b1, %2, 2;\n\t"
-      "add.u64 b2, %2, 4;\n\t"
-      "add.u64 b3, %2, 6;\n\t"
-      "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %4, p0;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l0], %2, %5, p1;\n\t"
-      "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [a1], b1, %4, p1;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l1], b1, %5, p1;\n\t"
-      "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], b2, %4, p1;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l2], b2, %5, p1;\n\t"
-      "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], b3, %4, p1;\n\t"
-      "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l3], b3, %5, p1;\n\t"
-      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
-      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
-      "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-      "}\n"
-      ::"r"(d_tmem), "r"(a_raw), "l"(bdesc), "r"(acc_first), "r"(idesc_full), "r"(idesc_half), "r"(bar_t), "r"(bar_b),
-        "r"(bar_acc), "r"(chunk_end), "r"(skip_lo), "n"(K)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
-      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout)
-// layout_type: 2 = SWIZZLE_128B (16-byte chunks, 8-row period), 1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row
-// period) -- the only shared-memory layout the tensor core accepts for MN-major 32-bit operands
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type = 2) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);               // [0,14)  start address >> 4
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;      // [16,30) leading byte offset >> 4
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;      // [32,46) stride byte offset >> 4
-  d |= (uint64_t)1 << 46;                                 // [46,48) descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;                       // [61,64) layout type
-  return d;
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major) {
-  return (1u << 4)                       // c_format = F32
-         | (2u << 7)                     // a_format = TF32
-         | (2u << 10)                    // b_format = TF32
-         | ((uint32_t)a_mn_major << 15)  // A major: 0 = K, 1 = MN
-         | (0u << 16)                    // B major: K
-         | ((uint32_t)(n >> 3) << 17)    // N >> 3
-         | ((uint32_t)(TC_BM >> 4) << 24);  // M >> 4
-}
-
-__device__ __forceinline__ float tf32_hi(float x, int mode) {
-  uint32_t u = __float_as_uint(x);
-  if (mode) u += 0x0FFFu + ((u >> 13) & 1u);   // round to nearest even (calibration fallback)
-  return __uint_as_float(u & 0xFFFFE000u);      // default: the tensor core drops the low 13 mantissa bits
-}
-
-// nearest tf32 with ties away from zero: 2 integer ops (the tie bias is ~3e-8 relative)
-__device__ __forceinline__ float tf32_round_up(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
-
-// cycle accounting for DNMF_TC_DBG & 16 (per-role time split written to a debug buffer; off in production)
-#define TC_T(var) do { if (prof) { const long long _n = clock64(); var += _n - tprev; tprev = _n; } } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
 // persistent tcgen05 kernel
@@ -593,11 +401,7 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
   return 0;
 }
 
-struct TcPlan {
-  int x_blocks, kt_total, kt_per_split, splits, num_units, grid;
-  int64_t ldb;            // leading dimension of Bcat (reduced length rounded up to 4)
-  int64_t bcat_bytes, partial_bytes;
-};
+}  // namespace
 
 TcPlan tc_plan(int64_t x_len, int64_t r_len, int k) {
   TcPlan p;
@@ -619,6 +423,8 @@ TcPlan tc_plan(int64_t x_len, int64_t r_len, int k) {
   p.partial_bytes = (int64_t)p.splits * x_len * k * 4;
   return p;
 }
+
+namespace {
 
 unsigned long long* g_prof = nullptr;   // debug: per-CTA role timings (dnmf_set_tc_profile)
 int g_hi_mode = -1;     // -1 unknown, 0 truncate, 1 round-to-nearest-even, 2 = tensor path unusable
@@ -748,9 +554,27 @@ bool device_is_sm100() {
 
 }  // namespace
 
+int tc_make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                CUtensorMapSwizzle swz) {
+  return make_map(map, ptr, rows, cols, ld, box_cols, box_rows, swz);
+}
+int tc_hi_mode() { return g_hi_mode; }
+unsigned long long* tc_prof_ptr() { return g_prof; }
+int tc_dbg_flags() { return getenv("DNMF_TC_DBG") ? atoi(getenv("DNMF_TC_DBG")) : 0; }
+void tc_launch_split_h(const float* H, int64_t ldh, float* Bcat, int64_t ldb, int k, int64_t n, cudaStream_t st) {
+  tc_split_h_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(H, ldh, Bcat, ldb, k, n);
+  tls().launches++;
+}
+void tc_launch_split_wt(const float* W, int64_t ldw, float* Bcat, int64_t ldb, int k, int64_t m, cudaStream_t st) {
+  tc_split_wt_kernel<<<(unsigned)ceil_div(m, 64), 256, 0, st>>>(W, ldw, Bcat, ldb, k, m);
+  tls().launches++;
+}
+
 bool tc_eligible(int op, const void* A, int64_t lda, int64_t m, int64_t n, int64_t k, int dtype) {
   if (tls().force_generic) return false;
-  if (op != DNMF_OP_AH && op != DNMF_OP_WTA) return false;       // KL path: generic kernels for now
+  const bool kl = (op == DNMF_OP_KL_UHT || op == DNMF_OP_KL_WTU);
+  if (op != DNMF_OP_AH && op != DNMF_OP_WTA && !kl) return false;
+  if (kl && !tc_kl_supported(k)) return false;
   if (dtype != DNMF_F32) return false;
   if (!(k == 16 || k == 32 || k == 64)) return false;
   if (((uintptr_t)A % 16) != 0 || (lda % 4) != 0) return false;
@@ -772,6 +596,7 @@ int64_t tc_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype) {
   if (dtype != DNMF_F32 || !(k == 16 || k == 32 || k == 64)) return 0;
   if (op == DNMF_OP_AH) { const TcPlan p = tc_plan(m, n, (int)k); return p.bcat_bytes + p.partial_bytes; }
   if (op == DNMF_OP_WTA) { const TcPlan p = tc_plan(n, m, (int)k); return p.bcat_bytes + p.partial_bytes; }
+  if ((op == DNMF_OP_KL_UHT || op == DNMF_OP_KL_WTU) && tc_kl_supported(k)) return tc_kl_workspace_bytes(op, m, n, k);
   return 0;
 }
 
@@ -785,13 +610,14 @@ int tc_wta(const float* A, int64_t lda, const float* W, int64_t ldw, float* Y, i
   return tc_run(1, A, lda, W, ldw, Y, ldy, m, n, k, transposed_out, g_hi_mode, ws, ws_bytes, st);
 }
 
-int tc_kl_uht(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int,
-              float, int, void*, int64_t, cudaStream_t) {
-  return fail(DNMF_E_UNSUPPORTED, "tcgen05 KL path not built");
+int tc_kl_uht(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* V, int64_t ldv,
+              int64_t m, int64_t n, int k, float eps, int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  return tc_kl_run(0, A, lda, W, ldw, H, ldh, V, ldv, m, n, k, eps, 0, ws, ws_bytes, st);
 }
-int tc_kl_wtu(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int,
-              float, int, int, void*, int64_t, cudaStream_t) {
-  return fail(DNMF_E_UNSUPPORTED, "tcgen05 KL path not built");
+int tc_kl_wtu(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* Y, int64_t ldy,
+              int64_t m, int64_t n, int k, float eps, int transposed_out, int math_mode, void* ws, int64_t ws_bytes,
+              cudaStream_t st) {
+  return tc_kl_run(1, A, lda, W, ldw, H, ldh, Y, ldy, m, n, k, eps, transposed_out, ws, ws_bytes, st);
 }
 
 }  // namespace dnmf

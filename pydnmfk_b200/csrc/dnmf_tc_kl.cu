@@ -1,0 +1,468 @@
+// Fused KL contractions on the tcgen05 path (fp32 data, k = 32):
+//
+//   UHT : V[m x k]   = (A / (W H + eps)) * H^T          (dist_nmf.py:338-339, :806,:810)
+//   WTU : Y^T[n x k] = (W^T * (A / (W H + eps)))^T      (dist_nmf.py:312-313, :806,:808)
+//
+// W H is never materialised.  Flash-attention-like structure per 128 x 32 tile of A (x = accumulator row: a row of A
+// for UHT, a column of A for WTU; r = the 32 reduced indices of the tile):
+//   GEMM1  S[x, r] = Fx[x, :] . Fr[r, :]        Fx = the x-side factor block (128 x k), resident in TENSOR MEMORY
+//                                                for the whole unit; Fr tile (32 x k, hi|lo) streamed by TMA
+//   U[x, r] = A[x, r] / (S[x, r] + eps)          splitter warps: A tile from smem, S from TMEM (tcgen05.ld)
+//   GEMM2  D[x, :] += U[x, r] . B[:, r]^T        exactly the FRO contraction with A replaced by U
+// Both GEMMs use the 3-term tf32 split (see dnmf_tc.cu) so the result is fp32-accurate; U and U_lo go to the TMEM
+// operand ring like A and A_lo do on the FRO path.  The MMA warp issues GEMM1 two tiles ahead of GEMM2.
+//
+// Warp roles (512 threads, one persistent CTA per SM): w0 A-TMA | w1 MMA issuer | w2-5, w11-14 splitter groups |
+// w6-9 drain | w10 Bcat-TMA | w15 Fr-TMA.
+#include "generic_passes.cuh"
+#include "tc_common.cuh"
+
+namespace dnmf {
+namespace {
+
+constexpr int KK = 32;            // factor width handled by this kernel
+constexpr int KL_THREADS = 512;
+constexpr int KL_CHUNK = 4;       // K-tiles accumulated in TMEM before the drain warps fold them into registers
+constexpr int KL_LOOK = 2;        // GEMM1 runs this many tiles ahead of GEMM2
+
+struct KlCfg {
+  static constexpr int N2 = 2 * KK;                    // 64
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;    // 16 KB
+  static constexpr int B_BYTES = N2 * TC_BK * 4;       // 8 KB  Bcat tile  [2k][32 r]
+  static constexpr int F_BYTES = N2 * KK * 4;          // 8 KB  FrCat tile [hi 32 r | lo 32 r][k]
+  static constexpr int SA = 6, SB = 6, SF = 6;
+  static constexpr int NBUF = 2, NT = 2, NS = 3;
+  static constexpr int ACC_COL0 = 0;
+  static constexpr int OP_COL0 = NBUF * N2;            // 128
+  static constexpr int S_COL0 = OP_COL0 + NT * 64;     // 256
+  static constexpr int FX_COL0 = S_COL0 + NS * 64;     // 448
+  static_assert(FX_COL0 + 64 <= 512, "TMEM has 512 columns");
+  static constexpr int NBARS = 2 * SA + 2 * SB + 2 * SF + 2 * NT + 2 * NS + 2 * NBUF + 2;
+  static constexpr int BAR_BYTES = 1024;
+  static_assert((NBARS + 1) * 8 <= BAR_BYTES, "barrier area too small");
+  static constexpr int SMEM_BYTES = SA * A_BYTES + SB * B_BYTES + SF * F_BYTES + 1024 + BAR_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory limit");
+};
+
+// MODE 0 (UHT): x = rows of A, A tile = TMA box {32 cols, 128 rows} with 128B swizzle, Fx = W rows
+// MODE 1 (WTU): x = columns of A, A tile = TMA box {128 cols, 32 rows} unswizzled,   Fx = H^T rows
+template <int MODE>
+__global__ void __launch_bounds__(KL_THREADS, 1)
+tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmF, const float* __restrict__ Fx, int64_t ldfx, int64_t fr_rows_pad,
+             float* __restrict__ P, int64_t split_stride, int64_t x_len, int x_blocks, int kt_total, int kt_per_split,
+             int num_units, int hi_mode, float eps, unsigned long long* __restrict__ prof) {
+  using Cfg = KlCfg;
+  constexpr int SA = Cfg::SA, SB = Cfg::SB, SF = Cfg::SF, NT = Cfg::NT, NS = Cfg::NS, NBUF = Cfg::NBUF, N2 = Cfg::N2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA0 = base, sB0 = sA0 + SA * Cfg::A_BYTES, sF0 = sB0 + SB * Cfg::B_BYTES;
+  const uint32_t bars = sF0 + SF * Cfg::F_BYTES;
+  int bi = 0;
+  const int iAF = bi; bi += SA;  const int iAE = bi; bi += SA;
+  const int iBF = bi; bi += SB;  const int iBE = bi; bi += SB;
+  const int iFF = bi; bi += SF;  const int iFE = bi; bi += SF;
+  const int iTF = bi; bi += NT;  const int iTE = bi; bi += NT;
+  const int iSF = bi; bi += NS;  const int iSE = bi; bi += NS;
+  const int iCF = bi; bi += NBUF; const int iCE = bi; bi += NBUF;
+  const int iXF = bi; bi += 1;   const int iXE = bi; bi += 1;
+  const int iSLOT = bi;
+  auto bar = [&](int idx) { return bars + 8u * idx; };
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      base_ptr + SA * Cfg::A_BYTES + SB * Cfg::B_BYTES + SF * Cfg::F_BYTES + 8 * iSLOT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmF);
+    for (int s = 0; s < SA; ++s) { mbar_init(bar(iAF + s), 1); mbar_init(bar(iAE + s), 4); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bar(iBF + s), 1); mbar_init(bar(iBE + s), 1); }
+    for (int s = 0; s < SF; ++s) { mbar_init(bar(iFF + s), 1); mbar_init(bar(iFE + s), 1); }
+    for (int s = 0; s < NT; ++s) { mbar_init(bar(iTF + s), 4); mbar_init(bar(iTE + s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(bar(iSF + s), 1); mbar_init(bar(iSE + s), 4); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(bar(iCF + b), 1); mbar_init(bar(iCE + b), 4); }
+    mbar_init(bar(iXF), 4);
+    mbar_init(bar(iXE), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(bar(iSLOT), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== A producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int xb = unit % x_blocks, sp = unit / x_blocks;
+        const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(bar(iAE + s), ph ^ 1u);
+          mbar_expect_tx(bar(iAF + s), Cfg::A_BYTES);
+          if (MODE == 0) tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, bar(iAF + s), kt * TC_BK, xb * TC_BM);
+          else tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, bar(iAF + s), xb * TC_BM, kt * TC_BK);
+          if (++s == SA) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== Bcat producer (GEMM2 B operand) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int sp = unit / x_blocks;
+        const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(bar(iBE + s), ph ^ 1u);
+          mbar_expect_tx(bar(iBF + s), Cfg::B_BYTES);
+          tma_load_2d(sB0 + s * Cfg::B_BYTES, &tmB, bar(iBF + s), kt * TC_BK, 0);
+          if (++s == SB) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 15) {
+    // ===================== FrCat producer (GEMM1 B operand): hi rows then lo rows of the 32 reduced indices =======
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int sp = unit / x_blocks;
+        const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(bar(iFE + s), ph ^ 1u);
+          mbar_expect_tx(bar(iFF + s), Cfg::F_BYTES);
+          tma_load_2d(sF0 + s * Cfg::F_BYTES, &tmF, bar(iFF + s), 0, kt * TC_BK);
+          tma_load_2d(sF0 + s * Cfg::F_BYTES + Cfg::F_BYTES / 2, &tmF, bar(iFF + s), 0, (int)fr_rows_pad + kt * TC_BK);
+          if (++s == SF) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, elected lane inside the asm blocks) =====================
+    constexpr uint32_t idesc_full = make_idesc(N2, 0);
+    constexpr uint32_t idesc_half = make_idesc(KK, 0);
+    int sf = 0, ss = 0, sb = 0, ts = 0, buf = 0;
+    uint32_t pf = 0, ps = 0, pb = 0, pt = 0, accphase = 0, pxu = 0;
+    const uint32_t fx_tmem = tmem_base + (uint32_t)Cfg::FX_COL0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int sp = unit / x_blocks;
+      const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
+      const int ntiles = kt1 - kt0;
+      mbar_wait(bar(iXF), pxu);                     // this unit's Fx block is in tensor memory
+      tc_fence_after();
+      // S = Fx . Fr^T for tile j:  cols [0,32) Fx_hi*Fr_hi ; cols [32,64) Fx_hi*Fr_lo + Fx_lo*Fr_hi
+      auto gemm1 = [&](int j) {
+        mbar_wait(bar(iFF + sf), pf);
+        mbar_wait(bar(iSE + ss), ps ^ 1u);
+        tc_fence_after();
+        umma_tile_ts<KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * 64), fx_tmem,
+                         make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), 0u, idesc_full, idesc_half,
+                         bar(iSF + ss), bar(iFE + sf), bar(iXE), (j == ntiles - 1) ? 1u : 0u, 0u);
+        if (++sf == SF) { sf = 0; pf ^= 1u; }
+        if (++ss == NS) { ss = 0; ps ^= 1u; }
+        __syncwarp();
+      };
+      const int pro = ntiles < KL_LOOK ? ntiles : KL_LOOK;
+      for (int j = 0; j < pro; ++j) gemm1(j);
+      for (int i = 0; i < ntiles; ++i) {
+        if (i + KL_LOOK < ntiles) gemm1(i + KL_LOOK);
+        const int in_chunk = i % KL_CHUNK;
+        if (in_chunk == 0) mbar_wait(bar(iCE + buf), accphase ^ 1u);
+        mbar_wait(bar(iTF + ts), pt);
+        mbar_wait(bar(iBF + sb), pb);
+        tc_fence_after();
+        const bool chunk_end = (in_chunk == KL_CHUNK - 1) || (i == ntiles - 1);
+        umma_tile_ts<KK>(tmem_base + (uint32_t)(Cfg::ACC_COL0 + buf * N2), tmem_base + (uint32_t)(Cfg::OP_COL0 + ts * 64),
+                         make_smem_desc(sB0 + sb * Cfg::B_BYTES, 16, 1024), in_chunk > 0 ? 1u : 0u, idesc_full, idesc_half,
+                         bar(iTE + ts), bar(iBE + sb), bar(iCF + buf), chunk_end ? 1u : 0u, 0u);
+        if (++ts == NT) { ts = 0; pt ^= 1u; }
+        if (++sb == SB) { sb = 0; pb ^= 1u; }
+        if (chunk_end) { if (++buf == NBUF) { buf = 0; accphase ^= 1u; } }
+        __syncwarp();
+      }
+      pxu ^= 1u;
+    }
+  } else if (warp < 6 || (warp >= 11 && warp < 15)) {
+    // ===================== splitters: A tile + S tile -> U = A / (S + eps) -> {U, U_lo} in TMEM ====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int group = (warp >= 11) ? 1 : 0;
+    int tile = 0;
+    uint32_t pxe = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int xb = unit % x_blocks, sp = unit / x_blocks;
+      const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
+      if (group == 0) {
+        // x-side factor row of this thread -> tensor memory (hi | lo), once per unit
+        mbar_wait(bar(iXE), pxe ^ 1u);              // the previous unit's GEMM1s have finished reading Fx
+        tc_fence_after();
+        const int64_t x = (int64_t)xb * TC_BM + r;
+        uint32_t hi[KK], lo[KK];
+        const float* frow = Fx + x * ldfx;
+#pragma unroll
+        for (int j = 0; j < KK; ++j) {
+          const float w = (x < x_len) ? frow[j] : 0.f;
+          const float h = tf32_hi(w, 1);
+          hi[j] = __float_as_uint(h);
+          lo[j] = __float_as_uint(tf32_round_up(w - h));
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::FX_COL0;
+        tmem_st_x32(taddr, hi);
+        tmem_st_x32(taddr + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(iXF));
+        pxe ^= 1u;
+      }
+      for (int kt = kt0; kt < kt1; ++kt, ++tile) {
+        if ((tile & 1) != group) continue;
+        const int sa = tile % SA, ts = tile % NT, ss = tile % NS;
+        const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u, ps = (uint32_t)(tile / NS) & 1u;
+        mbar_wait(bar(iAF + sa), pa);
+        const uint8_t* tl = base_ptr + sa * Cfg::A_BYTES;
+        uint32_t u[32], lo[32];
+        if (MODE == 0) {
+          const uint8_t* row = tl + r * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+            u[4 * c + 0] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
+          }
+        } else {
+          const uint8_t* col = tl + r * 4;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) u[j] = *reinterpret_cast<const uint32_t*>(col + j * 512);
+        }
+        // S tile of this accumulator row
+        mbar_wait(bar(iSF + ss), ps);
+        tc_fence_after();
+        const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::S_COL0 + ss * 64);
+#pragma unroll
+        for (int h0 = 0; h0 < 32; h0 += 16) {
+          uint32_t s0[16], s1[16];
+          tmem_ld_x16(saddr + h0, s0);
+          tmem_ld_x16(saddr + 32 + h0, s1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float den = (__uint_as_float(s0[j]) + __uint_as_float(s1[j])) + eps;
+            u[h0 + j] = __float_as_uint(__fdividef(__uint_as_float(u[h0 + j]), den));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(iSE + ss));          // S slot may be overwritten
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(u[j]);
+          lo[j] = __float_as_uint(tf32_round_up(v - tf32_hi(v, hi_mode)));
+        }
+        mbar_wait(bar(iTE + ts), pt ^ 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::OP_COL0 + ts * 64);
+        tmem_st_x32(taddr, u);
+        tmem_st_x32(taddr + 32, lo);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(iAE + sa));          // smem tile fully consumed (see dnmf_tc.cu)
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(iTF + ts));
+      }
+    }
+  } else {
+    // ===================== drain warps 6-9 =====================
+    const int q = warp & 3;
+    int buf = 0;
+    uint32_t accphase = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int xb = unit % x_blocks, sp = unit / x_blocks;
+      const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
+      const int nchunks = (kt1 - kt0 + KL_CHUNK - 1) / KL_CHUNK;
+      float acc[KK];
+#pragma unroll
+      for (int j = 0; j < KK; ++j) acc[j] = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(bar(iCF + buf), accphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COL0 + buf * N2);
+        uint32_t a[KK], b[KK];
+#pragma unroll
+        for (int j0 = 0; j0 < KK; j0 += 16) {
+          tmem_ld_x16(taddr + j0, *reinterpret_cast<uint32_t(*)[16]>(&a[j0]));
+          tmem_ld_x16(taddr + KK + j0, *reinterpret_cast<uint32_t(*)[16]>(&b[j0]));
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < KK; ++j) acc[j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(iCE + buf));
+        if (++buf == NBUF) { buf = 0; accphase ^= 1u; }
+      }
+      const int64_t x = (int64_t)xb * TC_BM + q * 32 + lane;
+      if (x < x_len) {
+        float* orow = P + (int64_t)sp * split_stride + x * KK;
+#pragma unroll
+        for (int j = 0; j < KK; j += 4)
+          *reinterpret_cast<float4*>(orow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// FrCat = [hi(F) ; lo(F)] for an r-side factor given as F[r][k] (rows = reduced indices), each half padded to r_pad rows
+// TRANS: the source is H [k x r] (row-major) and is transposed on the fly.
+template <bool TRANS>
+__global__ void __launch_bounds__(256) kl_split_fr_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ FrCat,
+                                                          int64_t r_len, int64_t r_pad, int k) {
+  __shared__ float tile[64][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 64;
+  if (TRANS) {
+    for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
+      const int j = idx / 64, r = idx % 64;                 // coalesced along r
+      tile[r][j] = (r0 + r < r_len) ? src[(int64_t)j * lds + r0 + r] : 0.f;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
+      const int r = idx / k, j = idx % k;
+      tile[r][j] = (r0 + r < r_len) ? src[(r0 + r) * lds + j] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
+    const int r = idx / k, j = idx % k;
+    if (r0 + r < r_pad) {
+      const float w = tile[r][j];
+      const float hi = tf32_hi(w, 1);
+      FrCat[(r0 + r) * k + j] = hi;
+      FrCat[(r_pad + r0 + r) * k + j] = tf32_round_up(w - hi);
+    }
+  }
+}
+
+// Ht[c][j] = H[j][c]
+__global__ void __launch_bounds__(256) kl_transpose_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Ht,
+                                                           int64_t n, int k) {
+  __shared__ float tile[64][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 64;
+  for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
+    const int j = idx / 64, c = idx % 64;
+    tile[c][j] = (c0 + c < n) ? H[(int64_t)j * ldh + c0 + c] : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
+    const int c = idx / k, j = idx % k;
+    if (c0 + c < n) Ht[(c0 + c) * k + j] = tile[c][j];
+  }
+}
+
+struct KlPlan {
+  TcPlan base;
+  int64_t r_pad, frcat_bytes, ht_bytes;
+};
+
+KlPlan kl_plan(int mode, int64_t m, int64_t n, int k) {
+  KlPlan p;
+  const int64_t x_len = mode == 0 ? m : n, r_len = mode == 0 ? n : m;
+  p.base = tc_plan(x_len, r_len, k);
+  p.r_pad = round_up(r_len, 64);
+  p.frcat_bytes = round_up(2 * p.r_pad * k * 4, 1024);
+  p.ht_bytes = round_up(n * (int64_t)k * 4, 1024);       // plain H^T (Fx of WTU; by-product for UHT)
+  return p;
+}
+
+}  // namespace
+
+bool tc_kl_supported(int64_t k) { return k == KK; }
+
+int64_t tc_kl_workspace_bytes(int op, int64_t m, int64_t n, int64_t k) {
+  const KlPlan p = kl_plan(op == DNMF_OP_KL_UHT ? 0 : 1, m, n, (int)k);
+  return p.base.bcat_bytes + p.frcat_bytes + p.ht_bytes + p.base.partial_bytes;
+}
+
+// ws = [Bcat | FrCat | Ht | partials]
+int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* out,
+              int64_t ldo, int64_t m, int64_t n, int k, float eps, int transposed_out, void* ws, int64_t ws_bytes,
+              cudaStream_t st) {
+  if (k != KK) return fail(DNMF_E_UNSUPPORTED, "tcgen05 KL path: k must be %d", KK);
+  const KlPlan kp = kl_plan(mode, m, n, k);
+  const TcPlan& pl = kp.base;
+  const int64_t x_len = mode == 0 ? m : n, r_len = mode == 0 ? n : m;
+  const int64_t need = pl.bcat_bytes + kp.frcat_bytes + kp.ht_bytes + pl.partial_bytes;
+  if (ws == nullptr || ws_bytes < need)
+    return fail(DNMF_E_WORKSPACE, "tcgen05 KL pass needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  if (((uintptr_t)ws % 256) != 0) return fail(DNMF_E_ARG, "workspace must be 256-byte aligned");
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  float* Bcat = reinterpret_cast<float*>(wsb);
+  float* FrCat = reinterpret_cast<float*>(wsb + pl.bcat_bytes);
+  float* Ht = reinterpret_cast<float*>(wsb + pl.bcat_bytes + kp.frcat_bytes);
+  float* P = reinterpret_cast<float*>(wsb + pl.bcat_bytes + kp.frcat_bytes + kp.ht_bytes);
+  const unsigned fr_blocks = (unsigned)ceil_div(kp.r_pad, 64);
+  const float* Fx;
+  int64_t ldfx;
+  if (mode == 0) {
+    // UHT: GEMM2 B = split(H); GEMM1 r-side factor = H^T rows (columns of A); x-side factor = W rows
+    tc_launch_split_h(H, ldh, Bcat, pl.ldb, k, n, st);
+    kl_split_fr_kernel<true><<<fr_blocks, 256, 0, st>>>(H, ldh, FrCat, r_len, kp.r_pad, k);
+    DNMF_LAUNCH_CHECK("kl_split_fr_kernel<T>");
+    Fx = W;
+    ldfx = ldw;
+  } else {
+    // WTU: GEMM2 B = split(W^T); GEMM1 r-side factor = W rows; x-side factor = H^T rows (columns of A)
+    tc_launch_split_wt(W, ldw, Bcat, pl.ldb, k, m, st);
+    kl_split_fr_kernel<false><<<fr_blocks, 256, 0, st>>>(W, ldw, FrCat, r_len, kp.r_pad, k);
+    DNMF_LAUNCH_CHECK("kl_split_fr_kernel<N>");
+    kl_transpose_kernel<<<(unsigned)ceil_div(n, 64), 256, 0, st>>>(H, ldh, Ht, n, k);    // plain H^T [n x k]
+    DNMF_LAUNCH_CHECK("kl_transpose_kernel");
+    Fx = Ht;
+    ldfx = k;
+  }
+  alignas(64) CUtensorMap tmA, tmB, tmF;
+  int rc;
+  if (mode == 0) rc = tc_make_map(&tmA, A, m, n, lda, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  else rc = tc_make_map(&tmA, A, m, n, lda, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
+  rc = tc_make_map(&tmB, Bcat, 2 * k, r_len, pl.ldb, TC_BK, 2 * k, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, k, k, k, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const int64_t split_stride = x_len * k;
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, KlCfg::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "tc_kl_kernel smem attribute");
+    kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmB, tmF, Fx, ldfx, kp.r_pad, P, split_stride, x_len,
+                                                          pl.x_blocks, pl.kt_total, pl.kt_per_split, pl.num_units,
+                                                          tc_hi_mode(), eps, tc_prof_ptr());
+    DNMF_LAUNCH_CHECK("tc_kl_kernel");
+    return 0;
+  };
+  rc = mode == 0 ? launch(tc_kl_kernel<0>) : launch(tc_kl_kernel<1>);
+  if (rc) return rc;
+  int64_t so_r, so_c;
+  if (mode == 0) { so_r = ldo; so_c = 1; }
+  else if (transposed_out) { so_r = ldo; so_c = 1; }
+  else { so_r = 1; so_c = ldo; }
+  reduce_partials_kernel<float><<<(unsigned)ceil_div(x_len * k, 256), 256, 0, st>>>(P, split_stride, pl.splits, x_len, k, out,
+                                                                                     so_r, so_c);
+  DNMF_LAUNCH_CHECK("reduce_partials_kernel");
+  return 0;
+}
+
+}  // namespace dnmf

@@ -108,3 +108,42 @@ def test_deterministic(ops):
     A, H = torch.rand((4096, 4096), device='cuda'), torch.rand((32, 4096), device='cuda')
     W = torch.rand((4096, 32), device='cuda')
     assert torch.equal(ops.ah(A, H), ops.ah(A, H)) and torch.equal(ops.wta(A, W), ops.wta(A, W))
+
+
+KL_SHAPES = [(128, 32, 32), (256, 96, 32), (1000, 1000, 32), (515, 2052, 32), (2048, 2048, 32), (4100, 300, 32),
+             (1024, 8192, 32), (8192, 1024, 32)]
+
+
+@pytest.mark.parametrize('m,n,k', KL_SHAPES)
+def test_kl_tensor_path(ops, m, n, k):
+    """Fused KL contractions on the tcgen05 path (k = 32): S = W H recomputed on the tensor cores, U = A / (S + eps)
+    in the splitter warps, second MMA; compared with float64 numpy and with the generic fused kernels."""
+    from pydnmfk_b200 import _lib as L
+    rs = np.random.RandomState(3)
+    A = rs.rand(m, n).astype(np.float32)
+    A[rs.rand(m, n) < 0.2] = 0                       # exact zeros must stay exact zeros in U
+    H, W = (rs.rand(k, n) + 0.05).astype(np.float32), (rs.rand(m, k) + 0.05).astype(np.float32)
+    eps = float(np.finfo(np.float32).eps)
+    f = np.float64
+    U = A.astype(f) / (W.astype(f) @ H.astype(f) + eps)
+    V = ops.kl_uht(_dev(A), _dev(W), _dev(H), eps).cpu().numpy()
+    assert L.last_path() == 1, 'tcgen05 KL path not taken'
+    Y = ops.kl_wtu(_dev(A), _dev(W), _dev(H), eps).cpu().numpy()
+    Yt = ops.kl_wtu(_dev(A), _dev(W), _dev(H), eps, transposed_out=True).cpu().numpy()
+    eV, eY = T.rel_fro(V, U @ H.astype(f).T), T.rel_fro(Y, W.astype(f).T @ U)
+    L.set_force_generic(True)
+    Vg = ops.kl_uht(_dev(A), _dev(W), _dev(H), eps).cpu().numpy()
+    Yg = ops.kl_wtu(_dev(A), _dev(W), _dev(H), eps).cpu().numpy()
+    L.set_force_generic(False)
+    gV, gY = T.rel_fro(Vg, U @ H.astype(f).T), T.rel_fro(Yg, W.astype(f).T @ U)
+    _diag('kl %dx%dx%d tc(V %.2e Y %.2e) generic(V %.2e Y %.2e)' % (m, n, k, eV, eY, gV, gY), V[:1, :1], V[:1, :1])
+    assert np.isfinite(V).all() and np.isfinite(Y).all()
+    assert eV <= 3e-6 and eY <= 3e-6, (eV, eY, gV, gY)
+    assert np.array_equal(Yt, Y.T)
+
+
+def test_kl_deterministic(ops):
+    A, H = torch.rand((4096, 4096), device='cuda'), torch.rand((32, 4096), device='cuda') + 0.1
+    W = torch.rand((4096, 32), device='cuda') + 0.1
+    assert torch.equal(ops.kl_uht(A, W, H, 1e-7), ops.kl_uht(A, W, H, 1e-7))
+    assert torch.equal(ops.kl_wtu(A, W, H, 1e-7), ops.kl_wtu(A, W, H, 1e-7))
