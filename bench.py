@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample', type=int, default=8192, help='side of the square CPU-baseline sample')
     ap.add_argument('--force-generic', action='store_true', help='disable the tcgen05 path (A/B runs)')
+    ap.add_argument('--no-graph', action='store_true', help='launch every step eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
 
@@ -208,6 +209,7 @@ def run_ours(args):
     from pydnmfk_b200 import device as D
     from pydnmfk_b200.dist_comm import MPI, MPI_comm
     from pydnmfk_b200.dist_nmf import nmf_algorithms_1D
+    from pydnmfk_b200.graphs import StepGraphs, graphs_enabled
     from pydnmfk_b200.pyDNMF import PyNMF
     from pydnmfk_b200.utils import parse, determine_block_params
 
@@ -267,17 +269,30 @@ def run_ours(args):
         W, H = W0.clone(), H0.clone()
         alg = nmf_algorithms_1D(A, W, H, params=p)
 
-        def step(i):
-            alg.update()
-            if i % 10 == 0:
-                ops.clamp_min(H, eps)
-                ops.clamp_min(W, eps)
+        def clamp():
+            ops.clamp_min(H, eps)
+            ops.clamp_min(W, eps)
 
+        sg = StepGraphs(alg.update, clamp) if (graphs_enabled(comm, 'mu') and not args.no_graph) else None
+
+        def step(i):
+            # the product's own loop body (PyNMF.fit): CUDA-graph replay of update() [+ clamp every 10th iteration]
+            if sg is not None:
+                sg.clamped() if i % 10 == 0 else sg.plain()
+            else:
+                alg.update()
+                if i % 10 == 0:
+                    clamp()
+
+        L.launch_count(reset=True)
+        alg.update()                       # eager step: sizes the workspace, counts the launches of one step
+        clamp()
+        launches_per_step = L.launch_count()
         for i in range(args.warmup):
             step(i)
         sync_all()
         L.launch_count(reset=True)
-        ops.timers = {}
+        ops.timers = {} if sg is None else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_a = time.perf_counter()
         e0.record()
@@ -288,8 +303,17 @@ def run_ours(args):
         t_b = time.perf_counter()
         windows.append((t_a, t_b))
         ms = e0.elapsed_time(e1)
-        launches += L.launch_count()
+        launches += launches_per_step * args.steps     # same launches per replayed step as in the eager one
         paths[norm] = 'tcgen05' if L.last_path() == 1 else 'generic'
+        if sg is not None:
+            # per-kernel CUDA events cannot be placed inside a replayed graph: time the same steps once more, eagerly,
+            # with an event pair around every A-streaming pass (not part of `value`)
+            ops.timers = {}
+            for i in range(min(args.steps, 10)):
+                alg.update()
+                if i % 10 == 0:
+                    clamp()
+            sync_all()
         pass_stats[norm] = ops.timer_summary()
         ops.timers = None
         if world > 1:
@@ -377,7 +401,9 @@ def run_ours(args):
             'config': {'workload': 'synthetic %dx%d fp32 non-negative, KL and FRO MU k=%d on %d B200 (grid %dx1, '
                                    'row shards of %d rows)' % (m, n, k, world, world, m_loc),
                        'l2': 'inputs larger than L2 (one A pass streams %.1f GiB per GPU)' % (pass_bytes / 2 ** 30),
-                       'norms': args.norms, 'math_mode': 'fp32-accurate', 'paths': paths},
+                       'norms': args.norms, 'math_mode': 'fp32-accurate', 'paths': paths,
+                       'launch': 'cuda-graph replay of update()+clamp (as PyNMF.fit does)' if not args.no_graph else 'eager',
+                       'roofline_timing': 'CUDA events around each A-streaming pass, eager replica of the timed steps' if not args.no_graph else 'CUDA events around each A-streaming pass inside the timed steps'},
             'by_norm': by_norm, 'roofline': roofline, 'cpu_baseline': cb, 'e2e': e2e, 'gpu_launches': int(launches),
             'clocks': clocks,
         }

@@ -434,8 +434,12 @@ template <int K, int MODE>
 int launch_pass(const CUtensorMap& tmA, const CUtensorMap& tmB, float* P, int64_t split_stride, int64_t x_len,
                 const TcPlan& pl, int hi_mode, cudaStream_t st) {
   auto kern = tc_pass_kernel<K, MODE>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<K>::SMEM_BYTES);
-  if (e != cudaSuccess) return cuda_fail(e, "tc_pass_kernel smem attribute");
+  static bool attr_set = false;      // once per instantiation (and never during a stream capture)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<K>::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "tc_pass_kernel smem attribute");
+    attr_set = true;
+  }
   kern<<<pl.grid, TcCfg<K>::THREADS, TcCfg<K>::SMEM_BYTES, st>>>(tmA, tmB, P, split_stride, x_len, pl.x_blocks, pl.kt_total,
                                                             pl.kt_per_split, pl.num_units, hi_mode,
                                                             getenv("DNMF_TC_DBG") ? atoi(getenv("DNMF_TC_DBG")) : 0, g_prof);

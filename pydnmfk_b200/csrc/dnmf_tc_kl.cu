@@ -445,8 +445,12 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   if (rc) return rc;
   const int64_t split_stride = x_len * k;
   auto launch = [&](auto kern) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, KlCfg::SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "tc_kl_kernel smem attribute");
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[mode]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, KlCfg::SMEM_BYTES);
+      if (e != cudaSuccess) return cuda_fail(e, "tc_kl_kernel smem attribute");
+      attr_set[mode] = true;
+    }
     kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmB, tmF, Fx, ldfx, kp.r_pad, P, split_stride, x_len,
                                                           pl.x_blocks, pl.kt_total, pl.kt_per_split, pl.num_units,
                                                           tc_hi_mode(), eps, tc_prof_ptr());

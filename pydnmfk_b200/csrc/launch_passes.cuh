@@ -46,9 +46,11 @@ int run_row_pass(const T* A, int64_t lda, const T* H, int64_t ldh, const T* W, i
   const Split sp = row_pass_plan<T, KP, KL>(m, n);
   const int vec_ok = (((uintptr_t)A % 16) == 0) && (lda % Cfg::VN == 0);
   auto kern = row_pass_kernel<T, KP, KL>;
-  if (Cfg::smem_bytes > 48 * 1024) {
+  static bool attr_set = false;
+  if (Cfg::smem_bytes > 48 * 1024 && !attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return cuda_fail(e, "row_pass smem attribute");
+    attr_set = true;
   }
   dim3 grid((unsigned)sp.blocks, (unsigned)sp.splits);
   if (sp.splits == 1) {

@@ -19,6 +19,7 @@ from . import device as D
 from .dist_nmf import nmf_algorithms_1D, nmf_algorithms_2D
 from .utils import data_operations, determine_block_params, var_init, comm_timing
 from .dist_comm import MPI
+from .graphs import StepGraphs, graphs_enabled
 
 
 def draw_rand_factors(topo, p_c, rank, a_shape, factor_shape, k, dt):
@@ -144,13 +145,26 @@ class PyNMF():
         Alg = nmf_algorithms_2D if self.topo == '2d' else nmf_algorithms_1D
         alg = Alg(self.A_ij, W, H, params=self.params)
         self._alg = alg
+        def clamp():                                                    # pyDNMF.py:155-157 / :170-172
+            self.ops.clamp_min(H, self.eps)
+            self.ops.clamp_min(W, self.eps)
+
+        # iteration 0 runs eagerly; the rest replay a captured CUDA graph of the same launches (see graphs.py)
+        use_graph = (self.itr >= 4 and var_init(self.params, 'cuda_graph', True)
+                     and graphs_enabled(self.comm1, self.method))
+        sg = StepGraphs(alg.update, clamp) if use_graph else None
         for i in range(self.itr):
             if self.method.lower() == 'bcd':
                 i = self.itr - 1                                        # pyDNMF.py:152
-            alg.update()
-            if i % 10 == 0:                                             # pyDNMF.py:155-157 / :170-172
-                self.ops.clamp_min(H, self.eps)
-                self.ops.clamp_min(W, self.eps)
+            if sg is not None and i >= 1:
+                if i % 10 == 0:
+                    sg.clamped()
+                else:
+                    sg.plain()
+            else:
+                alg.update()
+                if i % 10 == 0:
+                    clamp()
             if i == self.itr - 1:
                 W, H = self.normalize_features(W, H)
                 self._set_factors(W, H)
