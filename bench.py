@@ -15,6 +15,7 @@ Workload (BASELINE.json configs[1]): synthetic i.i.d. uniform(0,1) fp32 matrix, 
 grid N x 1 (row shards; the matrix is fixed as N grows => strong scaling), prune off, rand init.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -324,7 +325,9 @@ def run_ours(args):
         tot_ms += ms
         tot_it += args.steps
         assert torch.isfinite(W).all() and torch.isfinite(H).all()
-        del alg
+        del alg, sg, step, clamp      # captured graphs (with their NCCL nodes) must die before the process group does
+        gc.collect()
+        torch.cuda.synchronize()
 
     value = tot_it / (tot_ms / 1000.0)
 
@@ -409,8 +412,13 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Leave without tearing NCCL down: destroy_process_group() can block for minutes once collectives have been
+        # captured into CUDA graphs, and the JSON line is already out.  Every rank exits 0 right after a final barrier.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

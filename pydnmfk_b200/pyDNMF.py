@@ -174,6 +174,7 @@ class PyNMF():
                         print('relative error is:', self.recon_err)
                 if self.save_factors:
                     data_write(self.params).save_factors([W.cpu().numpy(), H.cpu().numpy()])  # noqa: F405
+                sg = None                      # drop the captured graphs (and their NCCL nodes) with the fit
                 if self.topo == '2d':
                     self.comm.Free()
                 if self.prune:
