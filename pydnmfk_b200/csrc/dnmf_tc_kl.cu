@@ -13,7 +13,7 @@
 // operand ring like A and A_lo do on the FRO path.  The MMA warp issues GEMM1 two tiles ahead of GEMM2.
 //
 // Warp roles (512 threads, one persistent CTA per SM): w0 A-TMA | w1 MMA issuer | w2-5, w11-14 splitter groups |
-// w6-9 drain | w10 Bcat-TMA | w15 Fr-TMA.
+// w6-9 drain | w10 Bcat-TMA (lane 0) + Fr-TMA (lane 1) | w15 GEMM1 issuer.
 #include "generic_passes.cuh"
 #include "tc_common.cuh"
 
@@ -23,7 +23,6 @@ namespace {
 constexpr int KK = 32;            // factor width handled by this kernel
 constexpr int KL_THREADS = 512;
 constexpr int KL_CHUNK = 4;       // K-tiles accumulated in TMEM before the drain warps fold them into registers
-constexpr int KL_LOOK = 2;        // GEMM1 runs this many tiles ahead of GEMM2
 
 struct KlCfg {
   static constexpr int N2 = 2 * KK;                    // 64
@@ -113,7 +112,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 10) {
-    // ===================== Bcat producer (GEMM2 B operand) =====================
+    // ===================== Bcat producer (lane 0, GEMM2 B operand) and FrCat producer (lane 1, GEMM1 B operand) =====
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
@@ -127,10 +126,8 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (++s == SB) { s = 0; ph ^= 1u; }
         }
       }
-    }
-  } else if (warp == 15) {
-    // ===================== FrCat producer (GEMM1 B operand): hi rows then lo rows of the 32 reduced indices =======
-    if (lane == 0) {
+    } else if (lane == 1) {
+      // hi rows then lo rows of the 32 reduced indices
       int s = 0;
       uint32_t ph = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -145,23 +142,24 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (converged warp, elected lane inside the asm blocks) =====================
+  } else if (warp == 15) {
+    // ===================== GEMM1 issuer: S = Fx . Fr^T, runs ahead of GEMM2 by up to NS tiles =====================
+    //   cols [0,32) Fx_hi*Fr_hi ; cols [32,64) Fx_hi*Fr_lo + Fx_lo*Fr_hi
     constexpr uint32_t idesc_full = make_idesc(N2, 0);
     constexpr uint32_t idesc_half = make_idesc(KK, 0);
-    int sf = 0, ss = 0, sb = 0, ts = 0, buf = 0;
-    uint32_t pf = 0, ps = 0, pb = 0, pt = 0, accphase = 0, pxu = 0;
+    int sf = 0, ss = 0;
+    uint32_t pf = 0, ps = 0, pxu = 0;
     const uint32_t fx_tmem = tmem_base + (uint32_t)Cfg::FX_COL0;
+    long long tprev = clock64(), t_g1wait = 0, t_g1 = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int sp = unit / x_blocks;
       const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
       const int ntiles = kt1 - kt0;
       mbar_wait(bar(iXF), pxu);                     // this unit's Fx block is in tensor memory
-      tc_fence_after();
-      // S = Fx . Fr^T for tile j:  cols [0,32) Fx_hi*Fr_hi ; cols [32,64) Fx_hi*Fr_lo + Fx_lo*Fr_hi
-      auto gemm1 = [&](int j) {
+      for (int j = 0; j < ntiles; ++j) {
         mbar_wait(bar(iFF + sf), pf);
         mbar_wait(bar(iSE + ss), ps ^ 1u);
+        TC_T(t_g1wait);
         tc_fence_after();
         umma_tile_ts<KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * 64), fx_tmem,
                          make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), 0u, idesc_full, idesc_half,
@@ -169,15 +167,30 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++sf == SF) { sf = 0; pf ^= 1u; }
         if (++ss == NS) { ss = 0; ps ^= 1u; }
         __syncwarp();
-      };
-      const int pro = ntiles < KL_LOOK ? ntiles : KL_LOOK;
-      for (int j = 0; j < pro; ++j) gemm1(j);
+        TC_T(t_g1);
+      }
+      pxu ^= 1u;
+    }
+    if (prof && lane == 0) { prof[blockIdx.x * 16 + 0] = t_g1wait; prof[blockIdx.x * 16 + 1] = t_g1; }
+  } else if (warp == 1) {
+    // ===================== GEMM2 issuer (converged warp, elected lane inside the asm block) =====================
+    constexpr uint32_t idesc_full = make_idesc(N2, 0);
+    constexpr uint32_t idesc_half = make_idesc(KK, 0);
+    int sb = 0, ts = 0, buf = 0;
+    uint32_t pb = 0, pt = 0, accphase = 0;
+    long long tprev = clock64(), t_acce = 0, t_tfull = 0, t_bfull = 0, t_g2 = 0, t0 = tprev;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int sp = unit / x_blocks;
+      const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
+      const int ntiles = kt1 - kt0;
       for (int i = 0; i < ntiles; ++i) {
-        if (i + KL_LOOK < ntiles) gemm1(i + KL_LOOK);
         const int in_chunk = i % KL_CHUNK;
         if (in_chunk == 0) mbar_wait(bar(iCE + buf), accphase ^ 1u);
+        TC_T(t_acce);
         mbar_wait(bar(iTF + ts), pt);
+        TC_T(t_tfull);
         mbar_wait(bar(iBF + sb), pb);
+        TC_T(t_bfull);
         tc_fence_after();
         const bool chunk_end = (in_chunk == KL_CHUNK - 1) || (i == ntiles - 1);
         umma_tile_ts<KK>(tmem_base + (uint32_t)(Cfg::ACC_COL0 + buf * N2), tmem_base + (uint32_t)(Cfg::OP_COL0 + ts * 64),
@@ -187,8 +200,12 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++sb == SB) { sb = 0; pb ^= 1u; }
         if (chunk_end) { if (++buf == NBUF) { buf = 0; accphase ^= 1u; } }
         __syncwarp();
+        TC_T(t_g2);
       }
-      pxu ^= 1u;
+    }
+    if (prof && lane == 0) {
+      prof[blockIdx.x * 16 + 2] = t_acce; prof[blockIdx.x * 16 + 3] = t_tfull; prof[blockIdx.x * 16 + 4] = t_bfull;
+      prof[blockIdx.x * 16 + 5] = t_g2; prof[blockIdx.x * 16 + 15] = clock64() - t0;
     }
   } else if (warp < 6 || (warp >= 11 && warp < 15)) {
     // ===================== splitters: A tile + S tile -> U = A / (S + eps) -> {U, U_lo} in TMEM ====================
@@ -197,6 +214,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int group = (warp >= 11) ? 1 : 0;
     int tile = 0;
     uint32_t pxe = 0;
+    long long tprev = clock64(), t_afull = 0, t_load = 0, t_sfull = 0, t_div = 0, t_tfree = 0, t_store = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int xb = unit % x_blocks, sp = unit / x_blocks;
       const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
@@ -227,7 +245,9 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if ((tile & 1) != group) continue;
         const int sa = tile % SA, ts = tile % NT, ss = tile % NS;
         const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u, ps = (uint32_t)(tile / NS) & 1u;
+        TC_T(t_store);
         mbar_wait(bar(iAF + sa), pa);
+        TC_T(t_afull);
         const uint8_t* tl = base_ptr + sa * Cfg::A_BYTES;
         uint32_t u[32], lo[32];
         if (MODE == 0) {
@@ -243,19 +263,23 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j) u[j] = *reinterpret_cast<const uint32_t*>(col + j * 512);
         }
         // S tile of this accumulator row
+        TC_T(t_load);
         mbar_wait(bar(iSF + ss), ps);
+        TC_T(t_sfull);
         tc_fence_after();
         const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::S_COL0 + ss * 64);
-#pragma unroll
-        for (int h0 = 0; h0 < 32; h0 += 16) {
-          uint32_t s0[16], s1[16];
-          tmem_ld_x16(saddr + h0, s0);
-          tmem_ld_x16(saddr + 32 + h0, s1);
+        {
+          uint32_t s0[32], s1[32];
+          tmem_ld_x32(saddr, s0);           // Fx_hi * Fr_hi
+          tmem_ld_x32(saddr + 32, s1);      // Fx_hi * Fr_lo + Fx_lo * Fr_hi
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 32; ++j) {
             const float den = (__uint_as_float(s0[j]) + __uint_as_float(s1[j])) + eps;
-            u[h0 + j] = __float_as_uint(__fdividef(__uint_as_float(u[h0 + j]), den));
+            const float a = __uint_as_float(u[j]);
+            // alternate SFU (MUFU.RCP) and FMA-pipe (Newton) reciprocals: the 32 divisions per thread and tile are the
+            // splitter's largest cost
+            u[j] = __float_as_uint((j & 1) ? div_newton(a, den) : __fdividef(a, den));
           }
         }
         tc_fence_before();
@@ -266,7 +290,9 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const float v = __uint_as_float(u[j]);
           lo[j] = __float_as_uint(tf32_round_up(v - tf32_hi(v, hi_mode)));
         }
+        TC_T(t_div);
         mbar_wait(bar(iTE + ts), pt ^ 1u);
+        TC_T(t_tfree);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::OP_COL0 + ts * 64);
         tmem_st_x32(taddr, u);
@@ -278,6 +304,10 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iTF + ts));
       }
+    }
+    if (prof && warp == 2 && lane == 0) {
+      prof[blockIdx.x * 16 + 6] = t_afull; prof[blockIdx.x * 16 + 7] = t_load; prof[blockIdx.x * 16 + 8] = t_sfull;
+      prof[blockIdx.x * 16 + 9] = t_div; prof[blockIdx.x * 16 + 10] = t_tfree; prof[blockIdx.x * 16 + 11] = t_store;
     }
   } else {
     // ===================== drain warps 6-9 =====================

@@ -67,3 +67,19 @@ if a.roles:
         for i, n in enumerate(names):
             if n and i != 15:
                 print('   %-22s %5.1f%%' % (n, 100 * v[:, i].mean() / tot))
+
+if a.roles and a.kl:
+    names = ['MMA gemm1 wait(Fr,S free)', 'MMA gemm1 issue', 'MMA wait acce', 'MMA wait t_full', 'MMA wait b_full', 'MMA gemm2 issue+loop',
+             'split wait a_full', 'split load A', 'split wait S', 'split ldtm+div+lo', 'split wait t_free', 'split store', '', '', '', 'total']
+    for nm, fn in (('kl_uht', lambda: ops.kl_uht(A, W, H, 1.2e-7)), ('kl_wtu', lambda: ops.kl_wtu(A, W, H, 1.2e-7))):
+        buf = torch.zeros(148 * 16, dtype=torch.int64, device='cuda')
+        L.call('dnmf_set_tc_profile', buf.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        L.call('dnmf_set_tc_profile', None)
+        v = buf.cpu().numpy().reshape(148, 16).astype(float)
+        tot = v[:, 15].mean()
+        print(nm, 'cycles per CTA %.0f' % tot)
+        for i, n in enumerate(names):
+            if n and i != 15:
+                print('   %-28s %5.1f%%' % (n, 100 * v[:, i].mean() / tot))
