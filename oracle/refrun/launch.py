@@ -27,9 +27,18 @@ def reference_available():
 def _child(rank, size, conns, result_conn, target, args):
     try:
         os.environ["OMP_NUM_THREADS"] = "1"
+        # the reference and the shims must win over anything of the same name in the parent process: the repo ships a
+        # `pyDNMFk` import alias of the product, which must never answer for the reference here
         for p in (REFERENCE, SHIMS):
-            if p not in sys.path:
-                sys.path.insert(0, p)
+            while p in sys.path:
+                sys.path.remove(p)
+            sys.path.insert(0, p)
+        for name in [n for n in sys.modules if n == 'pyDNMFk' or n.startswith('pyDNMFk.')
+                     or n.split('.')[0] in ('mpi4py', 'h5py', 'matplotlib')]:
+            del sys.modules[name]
+        import pyDNMFk as _ref_pkg
+        if not os.path.abspath(_ref_pkg.__file__).startswith(os.path.abspath(REFERENCE) + os.sep):
+            raise RuntimeError('reference harness imported %s instead of the reference' % _ref_pkg.__file__)
         import numpy as np
         if not hasattr(np, 'product'):
             np.product = np.prod

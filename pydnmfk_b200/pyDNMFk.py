@@ -112,17 +112,56 @@ class PyNMFk():
         self._A_dev = D.to_device(self.A_ij)
         self._numpy_in = not isinstance(self.A_ij, torch.Tensor)
 
+    def _spread(self):
+        return (bool(getattr(self.params, 'ensemble_parallel', False)) and self.params.comm1.size > 1
+                and self.p_r * self.p_c == 1)
+
+    def _enter_solo(self):
+        """Swap the communicators on ``params`` for a private size-1 grid (replica mode)."""
+        from .dist_comm import Comm, MPI_comm
+        world = self.params.comm1
+        saved = (self.params.comm1, self.params.comm, self.params.row_comm, self.params.col_comm)
+        solo = Comm([world.ranks[world.rank]], None)
+        grid = MPI_comm(solo, 1, 1)
+        self.params.comm1, self.params.comm = solo, grid
+        self.params.row_comm, self.params.col_comm = grid.cart_1d_row(), grid.cart_1d_column()
+        return saved
+
+    def _leave_solo(self, saved):
+        self.params.comm1, self.params.comm, self.params.row_comm, self.params.col_comm = saved
+
     def fit_ensemble(self, k):
-        """pyDNMFk.py:226-238 for one k."""
+        """pyDNMFk.py:226-238 for one k.
+
+        The reference runs the perturbations one after another on the whole grid.  With ``params.ensemble_parallel``
+        set and a 1x1 factorization grid inside a larger world (every rank holds the full matrix on its own GPU), the
+        perturbations are independent replicas: rank r takes perturbations r, r+size, ... on a private size-1
+        communicator (no data-path collective) and the factors are exchanged once at the end.  Results are identical to
+        the sequential order because every perturbation re-seeds its own RNG stream (seed = 1000 * perturbation).
+        """
         self.k = k
         self.params.k = k
-        results = []
-        for perturbation in range(self.perturbations):
+        world = self.params.comm1
+        spread = self._spread()
+        todo = list(range(self.perturbations))
+        saved = None
+        if spread:
+            todo = todo[world.rank::world.size]
+            saved = self._enter_solo()
+        mine = {}
+        for perturbation in todo:
             data = sample(data=self._A_dev, noise_var=self.noise_var, method=self.sampling,
                           seed=perturbation * 1000).fit()
             self.params.W_update = True
             W, H, err = PyNMF(data, factors=None, params=self.params).fit()
-            results.append((W.cpu().numpy(), H.cpu().numpy(), err))
+            mine[perturbation] = (W.cpu().numpy(), H.cpu().numpy(), err)
+        if spread:
+            self._leave_solo(saved)
+            merged = {}
+            for part in world.allgather(mine):
+                merged.update(part)
+            mine = merged
+        results = [mine[p] for p in range(self.perturbations)]
         self.Wall = np.hstack(([results[i][0] for i in range(self.perturbations)]))
         self.Wall = self.Wall.reshape(self.Wall.shape[0], self.k, self.perturbations, order='F')
         self.Hall = np.vstack(([results[i][1] for i in range(self.perturbations)]))
@@ -131,11 +170,15 @@ class PyNMFk():
         return self.Wall, self.Hall, self.recon_err
 
     def fit_regression(self, AvgW, AvgH):
-        """W-fixed fit from the cluster medians (pyDNMFk.py:245-248): only the H half-step runs."""
+        """W-fixed fit from the cluster medians (pyDNMFk.py:245-248): only the H half-step runs.  In replica mode
+        every rank runs the same (deterministic) fit on its own copy."""
         self.params.W_update = False
+        saved = self._enter_solo() if self._spread() else None
         reg = PyNMF(self._A_dev, factors=[AvgW, AvgH], params=self.params)
         W, H, err = reg.fit()
         self.col_err = reg.column_err()
+        if saved is not None:
+            self._leave_solo(saved)
         return W.cpu().numpy(), H.cpu().numpy(), err
 
     @comm_timing()

@@ -81,3 +81,25 @@ def test_data_operations_dims_single_rank():
     A = np.zeros((26, 14), dtype=np.float32)
     data_operations(A, p)
     assert (p.m, p.n, p.m_loc, p.n_loc, p.W_start, p.W_end, p.H_start, p.H_end) == (26, 14, 26, 14, 0, 26, 0, 14)
+
+
+def test_reference_import_surface():
+    """`from pyDNMFk.pyDNMF import *` style imports of the reference's tests resolve to this package and export the names
+    those tests use (tests/test_dist_nmf_1d.py:8-9,29,35 of the reference)."""
+    ns = {}
+    exec('from pyDNMFk.pyDNMF import *\nfrom pyDNMFk.dist_comm import *\nimport pyDNMFk.config as config', ns)
+    for name in ('PyNMF', 'np', 'MPI', 'MPI_comm', 'parse', 'determine_block_params', 'data_read', 'nmf_algorithms_1D',
+                 'nmf_algorithms_2D', 'var_init', 'data_operations'):
+        assert name in ns, name
+    ns['config'].init(0)
+    import pydnmfk_b200.pyDNMF as real
+    assert ns['PyNMF'] is real.PyNMF
+
+
+def test_cli_flag_surface():
+    import main as cli
+    import argparse
+    p = cli.parser_pyNMFk(cli.parser_pyNMF(argparse.ArgumentParser()))
+    a = p.parse_args(['--p_r', '2', '--p_c', '1'])
+    assert (a.k, a.itr, a.norm, a.method, a.prune, a.precision, a.init) == (4, 5000, 'kl', 'mu', False, 'float32', 'rand')
+    assert (a.perturbations, a.noise_var, a.start_k, a.end_k, a.step_k, a.sill_thr, a.sampling) == (20, 0.015, 1, 10, 1, 0.6, 'uniform')

@@ -159,3 +159,24 @@ def test_update_objects_accept_numpy_like_the_reference():
         with pytest.raises(Exception) as e:
             nmf_algorithms_1D(A, W.copy(), H.copy(), params=p).update()
         assert str(e.value) == bad[2]
+
+
+def test_ensemble_spread_over_ranks_equals_sequential():
+    """NMFk perturbation ensemble (pyDNMFk.py:226-238): spreading the perturbations over ranks gives exactly the
+    sequential stacking; the W-fixed regression fit (pyDNMFk.py:245-248) leaves W untouched up to normalisation."""
+    from oracle import nmf_oracle as O
+    seq = mp_util.run(1, workers.ensemble_worker, (False,), backend='gloo', timeout=600)[0]
+    par = mp_util.run(2, workers.ensemble_worker, (True,), backend='gloo', timeout=600)
+    for r in range(2):
+        assert np.array_equal(par[r]['Wall'], seq['Wall']) and np.array_equal(par[r]['Hall'], seq['Hall'])
+        assert par[r]['errs'] == seq['errs']
+    assert seq['Wall'].shape == (96, 3, 6) and seq['Hall'].shape == (3, 21, 6)
+    # oracle replay of perturbation 2 (seed 2000): noise, then init from the same stream (SURVEY A8)
+    rs = np.random.RandomState(5)
+    A = (rs.rand(96, 21) * 100).astype(np.float32)
+    rng = np.random.RandomState(2000)
+    X = O.perturb(A, 0.015, 'uniform', rng)
+    ref = O.fit([X], 1, 1, 3, 'kl', 'mu', 30, rngs=[rng], prune=True)[0]
+    assert T.rel_fro(seq['Wall'][:, :, 2], ref[0]) <= 1e-4 and T.rel_fro(seq['Hall'][:, :, 2], ref[1]) <= 1e-4
+    assert abs(seq['errs'][2] - float(ref[2])) <= 1e-5 * float(ref[2])
+    assert np.isfinite(seq['col_err']).all() and seq['col_err'].shape == (21,)

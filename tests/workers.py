@@ -125,3 +125,29 @@ def fit_many_worker(rank, world, cases, force_generic=False):
         if MPI.COMM_WORLD.allreduce(ok) != world:
             break   # stop the batch on every rank together
     return out
+
+
+def ensemble_worker(rank, world, spread):
+    """PyNMFk.fit_ensemble + fit_regression on wtsi-sized data: sequential, or spread over the ranks (replica mode)."""
+    import torch
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm, Comm
+    from pydnmfk_b200.pyDNMFk import PyNMFk
+    from pydnmfk_b200.utils import parse
+    torch.cuda.set_device(0)
+    comm = MPI.COMM_WORLD
+    solo = Comm([comm.ranks[comm.rank]], None)
+    g = MPI_comm(solo, 1, 1)
+    rs = np.random.RandomState(5)
+    A = (rs.rand(96, 21) * 100).astype(np.float32)
+    p = parse()
+    p.comm1 = comm if spread else solo
+    p.ensemble_parallel = bool(spread)
+    p.comm, p.row_comm, p.col_comm = g, g.cart_1d_row(), g.cart_1d_column()
+    p.p_r, p.p_c, p.init, p.verbose, p.itr, p.norm, p.method, p.prune = 1, 1, 'rand', False, 30, 'kl', 'mu', True
+    p.perturbations, p.noise_var, p.sampling = 6, 0.015, 'uniform'
+    nmfk = PyNMFk(A, params=p)
+    Wall, Hall, errs = nmfk.fit_ensemble(3)
+    AvgW, AvgH = Wall[:, :, 0], np.median(Hall, axis=-1)
+    Wr, Hr, er = nmfk.fit_regression(AvgW, AvgH)
+    return dict(Wall=Wall, Hall=Hall, errs=[float(e) for e in errs], Wr=Wr, Hr=Hr, er=float(er),
+                col_err=np.asarray(nmfk.col_err))
