@@ -348,8 +348,17 @@ def run_ours(args):
             per_kernel['%s:%s' % (norm, opn)] = {'launches': cnt, 'mean_ms': mean_ms, 'GBps': gbs, 'frac': gbs / peak}
             if dom is None or cnt * mean_ms > dom[1]:
                 dom = ('%s:%s' % (norm, opn), cnt * mean_ms, gbs)
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (same shard shape only)
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        if dom and (cap['m_loc'], cap['n'], cap['k']) == (m_loc, n, k) and dom[0] in cap['kernels']:
+            traffic = cap['kernels'][dom[0]]['dram_bytes_per_launch']
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'achieved': dom[2] if dom else None, 'peak': peak, 'unit': 'GB/s',
-                'frac': (dom[2] / peak) if dom else None, 'traffic': None, 'kernel': dom[0] if dom else None,
+                'frac': (dom[2] / peak) if dom else None, 'traffic': traffic,
+                'traffic_source': 'profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)' if traffic else None, 'kernel': dom[0] if dom else None,
                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': pass_bytes, 'per_kernel': per_kernel,
                 'iteration_frac_of_A_streaming_roofline': {
                     nm: (2.0 * pass_bytes / (v['ms_per_step'] * 1e-3) / 1e9) / peak for nm, v in by_norm.items()}}

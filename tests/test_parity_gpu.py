@@ -177,6 +177,9 @@ def test_ensemble_spread_over_ranks_equals_sequential():
     rng = np.random.RandomState(2000)
     X = O.perturb(A, 0.015, 'uniform', rng)
     ref = O.fit([X], 1, 1, 3, 'kl', 'mu', 30, rngs=[rng], prune=True)[0]
-    assert T.rel_fro(seq['Wall'][:, :, 2], ref[0]) <= 1e-4 and T.rel_fro(seq['Hall'][:, :, 2], ref[1]) <= 1e-4
+    # (Hall is the reference's vstack + C-order reshape, pyDNMFk.py:236-237: perturbation p is rows [p k, (p+1) k) of
+    #  the (P k, n) stack, not the slice [:, :, p])
+    H2 = seq['Hall'].reshape(6 * 3, 21)[2 * 3:3 * 3]
+    assert T.rel_fro(seq['Wall'][:, :, 2], ref[0]) <= 1e-4 and T.rel_fro(H2, ref[1]) <= 1e-4
     assert abs(seq['errs'][2] - float(ref[2])) <= 1e-5 * float(ref[2])
     assert np.isfinite(seq['col_err']).all() and seq['col_err'].shape == (21,)
