@@ -545,7 +545,7 @@ def relative_err(st):
 
 
 def fit(A_blocks, p_r, p_c, k, norm='kl', method='mu', itr=5000, rngs=None,
-        factors=None, prune=True, W_update=True, init='rand', return_state=False):
+        factors=None, prune=True, W_update=True, init='rand', return_state=False, py_rng=None):
     """PyNMF(A_ij, factors, params).fit() on every virtual rank.
 
     ``A_blocks``: list of per-rank shards (world-rank order, all one dtype).
@@ -568,8 +568,14 @@ def fit(A_blocks, p_r, p_c, k, norm='kl', method='mu', itr=5000, rngs=None,
         st.H = [np.asarray(f[1]).astype(st.dt) for f in factors]
     elif init == 'rand':
         st.W, st.H = init_factors_rand(st.A, grid, sh, st.k, rngs)
+    elif init == 'nnsvd':                                         # pyDNMF.py:131-135 (float64 factors, not cast)
+        if sh.topo != '1d':
+            raise Exception('NNSVD init only available for 1D topology, please try with 1d topo.')
+        from . import nmfk_oracle
+        wh = nmfk_oracle.nnsvd(st.A, sh.m[0], sh.n[0], st.k, p_r, p_c, st.eps, py_rng)
+        st.W, st.H = [w for w, _ in wh], [h for _, h in wh]
     else:
-        raise NotImplementedError('oracle: only rand init / given factors (nnsvd is row N1)')
+        raise ValueError(init)
     masks = None
     if prune:
         masks = zero_idx_prune(st.A, grid, sh)

@@ -1,2 +1,10 @@
-"""Call-swallowing ``matplotlib`` stub (plot_results.py:2-3 imports it at
-module scope).  TEST INFRASTRUCTURE ONLY."""
+"""Call-swallowing ``matplotlib`` stub (plot_results.py:2-3 imports it at module scope).  TEST INFRASTRUCTURE ONLY."""
+from unittest.mock import MagicMock
+
+rcParams = MagicMock()
+
+
+def __getattr__(name):
+    if name.startswith('__'):
+        raise AttributeError(name)
+    return MagicMock()
