@@ -191,6 +191,57 @@ int dnmf_scatter_cols(const void* X, int64_t ldx, const int64_t* col_idx, int64_
 int dnmf_perturb_uniform(const void* A, const void* U, void* X, int64_t count, double noise_var,
                          int dtype, void* stream);
 
+/* ==== NMFk-level rows =======================================================
+ * Ensemble tensors are C-contiguous: W_all [m_loc, k, P], H_all [k, n_loc, P] (P = perturbations).
+ *
+ * dnmf_colsumsq: out[j] = sum_i X[i][j]^2 (wide matrices, e.g. the m x (k P) view of W_all)
+ *                                             dist_clustering.py:33 (W_all*W_all).sum(axis=0), :120 (centroids**2).sum(0)
+ * dnmf_colsum_workspace_bytes: scratch of dnmf_colsum / dnmf_colsumsq for a rows x cols input
+ * dnmf_scale_groups: X[i0,i1,i2] op= f(s[i0*s0 + i1*s1 + i2*s2]) on a contiguous [d0,d1,d2] tensor;
+ *   mode 0: *= s   1: /= s   2: /= sqrt(s+eps)   3: *= sqrt(s+eps)   4: /= (s+eps)   5: *= (s+eps)
+ *                                             dist_clustering.py:36-39, :123-125 ; dist_svd.py:72-77
+ * dnmf_greedy_lsa: the greedy assignment + change_order of dist_clustering.py:49-69 for all P perturbations at
+ *   once; D [k, k*P] holds centroid-feature similarities at D[r*ldd + c*P + p]; order[p*k + r] = c (int32)
+ * dnmf_permute_groups: out[.., r, .., p] = in[.., src(p, r), .., p] along axis 0 or 1 of [d0, d1, P];
+ *   sequential = 0: src = order[p][r], the gather W_sub[:, j] of dist_clustering.py:81;
+ *   sequential = 1: the outcome of `for r: X[r] = X[order[p][r]]` done in place, which is what the list-of-views
+ *   assignment to H_all[:, :, p] (dist_clustering.py:116) amounts to under numpy >= 1.20 (rows already overwritten
+ *   are read back: src(r) = j[r] if j[r] >= r else src(j[r]))
+ * dnmf_median_last: med[row] = np.median(X[row, :P]); mad[row] = median(|X[row,:] - med[row]|) (either may be NULL)
+ *                                             dist_clustering.py:118 ; :41-47 (mad, flag=1) ; pyDNMFk.py:241
+ * dnmf_silhouettes: out[kk*P + n] (float64) from the (k P) x (k P) cosine Gram   dist_clustering.py:146-159
+ */
+int dnmf_colsumsq(const void* X, int64_t ldx, int64_t rows, int64_t cols, void* out,
+                  int dtype, void* ws, int64_t ws_bytes, void* stream);
+int64_t dnmf_colsum_workspace_bytes(int64_t rows, int64_t cols);
+int dnmf_scale_groups(void* X, int64_t d0, int64_t d1, int64_t d2, const void* s, int64_t s0, int64_t s1, int64_t s2,
+                      int mode, double eps, int dtype, void* stream);
+int dnmf_greedy_lsa(const void* D, int64_t ldd, int64_t k, int64_t P, int32_t* order, int dtype, void* stream);
+int dnmf_permute_groups(const void* in, void* out, int64_t d0, int64_t d1, int64_t P, int axis, const int32_t* order,
+                        int sequential, int dtype, void* stream);
+int dnmf_median_last(const void* X, int64_t rows, int64_t P, void* med, void* mad, int dtype, void* stream);
+int dnmf_silhouettes(const void* G, int64_t ldg, int64_t k, int64_t P, double* out, int dtype, void* stream);
+
+/* ---- nnsvd initialisation (dist_svd.py) ---------------------------------------------------------
+ * dnmf_rank1_sub:  M = (T)(M - sigma (u v^T)) with float64 u, v, sigma[0] (deflation)         dist_svd.py:160-162
+ * dnmf_matvec_f64: y = A x (trans = 0) or y = A^T x (trans = 1); A of `dtype`, x / y / accumulation float64
+ *                  (B @ currV: dist_svd.py:121 ; A @ v, A.T @ u: :166,:172)
+ * dnmf_power_normalize: v_out = y / ||y||, r[0] = <v_out, v_last>                              dist_svd.py:123-124
+ * dnmf_div_store:  dst[i*stride] = src[i] / sqrt(sq[0])    (u = u_unnorm / sig)                dist_svd.py:168,:174
+ * dnmf_posneg_colsumsq: out[j] = sum max(X[:,j],0)^2, out[k+j] = sum max(-X[:,j],0)^2          dist_svd.py:222-235
+ * dnmf_nnsvd_pick: out = pos[j] ? cp[j] max(X,0) / dp[j] : cn[j] max(-X,0) / dn[j], coef = [cp|dp|cn|dn]   :241-242
+ */
+int dnmf_rank1_sub(void* M, int64_t ldm, int64_t rows, int64_t cols, const double* u, const double* v, const double* sigma,
+                   int dtype, void* stream);
+int64_t dnmf_matvec_workspace_bytes(int64_t rows, int64_t cols, int trans);
+int dnmf_matvec_f64(const void* A, int64_t lda, int64_t rows, int64_t cols, const double* x, double* y, int trans,
+                    int dtype, void* ws, int64_t ws_bytes, void* stream);
+int dnmf_power_normalize(const double* y, const double* v_last, double* v_out, double* r, int64_t d, void* stream);
+int dnmf_div_store(const double* src, const double* sq, double* dst, int64_t n, int64_t stride, void* stream);
+int dnmf_posneg_colsumsq(const double* X, int64_t ldx, int64_t rows, int64_t k, double* out, void* stream);
+int dnmf_nnsvd_pick(const double* X, int64_t ldx, int64_t rows, int64_t k, const double* coef, const int32_t* pos,
+                    double* out, int64_t ldo, int transpose_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

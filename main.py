@@ -3,8 +3,8 @@
     python main.py --p_r=1 --p_c=1 --k=4 --fpath=data/ --fname=swim --ftype=mat --init=rand --itr=1000 --norm=fro --method=mu
     torchrun --nproc-per-node 4 main.py --p_r=4 --p_c=1 ...         (one process per GPU instead of mpirun -n 4)
 
-`--process=pyDNMFk` runs the perturbation ensemble for every k and reports the reconstruction errors; clustering and
-rank selection are not part of this build."""
+`--process=pyDNMFk` runs NMFk (perturbation ensemble, clustering, silhouettes, regression fit, rank selection) for
+k = start_k .. end_k and prints the estimated rank."""
 import argparse
 import sys
 
@@ -89,13 +89,11 @@ def main(argv=None):
         print('Reading data complete')
     if args.process == 'pyDNMFk':
         if rank == 0:
-            print('Starting PyDNMFk ensemble...')
-        nmfk = PyNMFk(A_ij, factors=None, params=args)
-        for k in range(args.start_k, args.end_k + 1, args.step_k):
-            Wall, Hall, errs = nmfk.fit_ensemble(k)
-            if rank == 0:
-                print('k=%d: %d perturbations, mean recon_err=%.6f' % (k, len(errs), float(sum(map(float, errs)) / len(errs))))
-        return None
+            print('Starting PyDNMFk...')
+        nopt = PyNMFk(A_ij, factors=None, params=args).fit()
+        if rank == 0:
+            print('PyDNMFk done.')
+        return nopt
     if rank == 0:
         print('Starting PyDNMF...')
     W, H, err = PyNMF(A_ij, factors=None, params=args).fit()

@@ -8,3 +8,8 @@ def __getattr__(name):
     if name.startswith('__'):
         raise AttributeError(name)
     return MagicMock()
+
+
+import importlib  # noqa: E402
+
+pyplot = importlib.import_module('.pyplot', __name__)   # the real stub module, not a mock attribute

@@ -56,10 +56,26 @@ SIGNATURES = {
     'dnmf_scatter_rows': (i32, [vp, i64, vp, i64, i64, vp, i64, i32, vp]),
     'dnmf_scatter_cols': (i32, [vp, i64, vp, i64, i64, vp, i64, i32, vp]),
     'dnmf_perturb_uniform': (i32, [vp, vp, vp, i64, dbl, i32, vp]),
+    # NMFk-level rows
+    'dnmf_colsumsq': (i32, [vp, i64, i64, i64, vp, i32, vp, i64, vp]),
+    'dnmf_colsum_workspace_bytes': (i64, [i64, i64]),
+    'dnmf_scale_groups': (i32, [vp, i64, i64, i64, vp, i64, i64, i64, i32, dbl, i32, vp]),
+    'dnmf_greedy_lsa': (i32, [vp, i64, i64, i64, vp, i32, vp]),
+    'dnmf_permute_groups': (i32, [vp, vp, i64, i64, i64, i32, vp, i32, i32, vp]),
+    'dnmf_median_last': (i32, [vp, i64, i64, vp, vp, i32, vp]),
+    'dnmf_silhouettes': (i32, [vp, i64, i64, i64, vp, i32, vp]),
+    'dnmf_rank1_sub': (i32, [vp, i64, i64, i64, vp, vp, vp, i32, vp]),
+    'dnmf_matvec_workspace_bytes': (i64, [i64, i64, i32]),
+    'dnmf_matvec_f64': (i32, [vp, i64, i64, i64, vp, vp, i32, i32, vp, i64, vp]),
+    'dnmf_power_normalize': (i32, [vp, vp, vp, vp, i64, vp]),
+    'dnmf_div_store': (i32, [vp, vp, vp, i64, i64, vp]),
+    'dnmf_posneg_colsumsq': (i32, [vp, i64, i64, i64, vp, vp]),
+    'dnmf_nnsvd_pick': (i32, [vp, i64, i64, i64, vp, vp, vp, i64, i32, vp]),
 }
 
 _NO_STATUS = {'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
-              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile'}
+              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile', 'dnmf_colsum_workspace_bytes',
+              'dnmf_matvec_workspace_bytes'}
 
 
 class DnmfError(RuntimeError):

@@ -263,6 +263,18 @@ int dnmf_colsum(const void* X, int64_t ldx, int64_t rows, int64_t cols, void* ou
   return sum_rows_of(X, ldx, rows, cols, out, 0, 0, dtype, ws, ws_bytes, stream);
 }
 
+int dnmf_colsumsq(const void* X, int64_t ldx, int64_t rows, int64_t cols, void* out, int dtype, void* ws,
+                  int64_t ws_bytes, void* stream) {
+  if (dtype != DNMF_F32 && dtype != DNMF_F64) return fail(DNMF_E_ARG, "dtype must be DNMF_F32 or DNMF_F64");
+  DNMF_CHECK_ARG(rows >= 0 && cols >= 0 && X && out, "shape / null pointer");
+  if (cols == 0) return 0;
+  return sum_rows_of(X, ldx, rows, cols, out, 0, 1, dtype, ws, ws_bytes, stream);
+}
+
+int64_t dnmf_colsum_workspace_bytes(int64_t rows, int64_t cols) {
+  return sum_plan(rows, 64, 1024).chunks * (cols > 0 ? cols : 1) * (int64_t)sizeof(double);
+}
+
 int dnmf_rowsum(const void* X, int64_t ldx, int64_t rows, int64_t cols, void* out, int dtype, void* ws,
                 int64_t ws_bytes, void* stream) {
   if (int rc = check_common(rows, cols, 0, dtype)) return rc;

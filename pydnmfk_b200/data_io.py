@@ -100,5 +100,81 @@ class data_write():
             np.save(self.fpath + wdir + 'W_' + str(self.rank), W)
             np.save(self.fpath + hdir + 'H_' + str(self.rank), H)
 
+    @comm_timing()
     def save_cluster_results(self, params):
-        raise NotImplementedError('results.h5 output needs h5py (SURVEY section 8f, row N3)')
+        """Per-k NMFk statistics on rank 0 (data_io.py:199-209): ``results.h5`` with the reference's dataset names when
+        ``h5py`` is importable, else the same names in ``results.npz`` (this image ships no h5py)."""
+        if self.rank == 0:
+            write_results(self.fpath, {
+                'clusterSilhouetteCoefficients': params['clusterSilhouetteCoefficients'],
+                'avgSilhouetteCoefficients': params['avgSilhouetteCoefficients'],
+                'L_err': params['L_err'], 'L_errDist': params['L_errDist'], 'avgErr': params['avgErr'],
+                'ErrTol': params['recon_err'], 'AIC': params['AIC']})
+
+
+def _h5py():
+    try:
+        import h5py
+        return h5py
+    except ImportError:
+        return None
+
+
+def write_results(dirpath, datasets):
+    h5 = _h5py()
+    if h5 is not None:
+        with h5.File(dirpath + 'results.h5', 'w') as hf:
+            for name, val in datasets.items():
+                hf.create_dataset(name, data=val)
+    else:
+        np.savez(dirpath + 'results.npz', **{k: np.asarray(v) for k, v in datasets.items()})
+
+
+def read_results(dirpath):
+    """{dataset name: ndarray} of one k's ``results.h5`` / ``results.npz`` (pyDNMFk.py:278, plot_results.py:117)."""
+    h5 = _h5py()
+    if h5 is not None and os.path.exists(os.path.join(dirpath, 'results.h5')):
+        with h5.File(os.path.join(dirpath, 'results.h5'), 'r') as hf:
+            return {k: np.array(hf[k]) for k in hf.keys()}
+    with np.load(os.path.join(dirpath, 'results.npz')) as z:
+        return {k: z[k] for k in z.files}
+
+
+class read_factors():
+    """Reassemble the regression factors written by ``save_factors(reg=True)`` (data_io.py:212-261).  The H blocks of
+    a 2-D grid are concatenated in the order the shards really cover the columns, (j, i); the reference's
+    ``transform_H_index`` formula is only right for square grids."""
+
+    @comm_timing()
+    def __init__(self, factors_path, pgrid):
+        self.factors_path = factors_path
+        self.W_path = self.factors_path + 'W_reg_factors/*'
+        self.H_path = self.factors_path + 'H_reg_factors/*'
+        self.p_grid = pgrid
+        self.load_factors()
+
+    def custom_read_npy(self, fpath):
+        return np.load(fpath)
+
+    def read_factor(self, fpath):
+        import glob
+        files = glob.glob(fpath)
+        if len(files) == 1:
+            return self.custom_read_npy(files[0]), 1
+        key = lambda f: int(os.path.splitext(os.path.basename(f))[0].split('_')[-1])   # noqa: E731  (W_10 after W_9)
+        return [self.custom_read_npy(f) for f in sorted(files, key=key)], len(files)
+
+    @comm_timing()
+    def load_factors(self):
+        W_data, ct_W = self.read_factor(self.W_path)
+        H_data, ct_H = self.read_factor(self.H_path)
+        if ct_W > 1:
+            W_data = np.vstack(W_data)
+        if ct_H > 1:
+            if ct_W > 1:
+                p_r, p_c = self.p_grid
+                H_data = np.hstack([H_data[i * p_c + j] for j in range(p_c) for i in range(p_r)])
+            else:
+                H_data = np.hstack(H_data)
+        self.W, self.H = W_data, H_data
+        return W_data, H_data

@@ -335,6 +335,123 @@ class DeviceOps:
                _DT[A.dtype], self._stream())
         return X
 
+    # ---- NMFk-level rows: clustering / silhouettes (dist_clustering.py) -------------------------------
+    def colsum_wide(self, X, squares=False):
+        """Column sums (or sums of squares) of a matrix with any number of columns (the m x kP view of W_all)."""
+        r, c = X.shape
+        out = self.empty((c,), X.dtype)
+        nb = L.call('dnmf_colsum_workspace_bytes', r, c)
+        ws = self.workspace(nb)
+        L.call('dnmf_colsumsq' if squares else 'dnmf_colsum', X.data_ptr(), _ld(X), r, c, out.data_ptr(), _DT[X.dtype],
+               ws, max(nb, self._ws_bytes), self._stream())
+        return out
+
+    def scale_groups(self, X, s, s_strides, mode, eps=0.0):
+        """In place X[i0,i1,i2] op= f(s[...]); X contiguous 3-D (2-D inputs are viewed as [1, d0, d1])."""
+        assert X.is_contiguous() and s.is_contiguous() and s.dtype == X.dtype
+        d = list(X.shape)
+        while len(d) < 3:
+            d.insert(0, 1)
+            s_strides = (0,) + tuple(s_strides)
+        L.call('dnmf_scale_groups', X.data_ptr(), d[0], d[1], d[2], s.data_ptr(), int(s_strides[0]), int(s_strides[1]),
+               int(s_strides[2]), int(mode), float(eps), _DT[X.dtype], self._stream())
+        return X
+
+    def greedy_lsa(self, Dm, k, P):
+        """order[p, r] = feature of perturbation p assigned to centroid r (int32 [P, k])."""
+        assert Dm.shape == (k, k * P)
+        order = self.empty((P, k), torch.int32)
+        L.call('dnmf_greedy_lsa', Dm.data_ptr(), _ld(Dm), k, P, order.data_ptr(), _DT[Dm.dtype], self._stream())
+        return order
+
+    def permute_groups(self, X, order, axis, sequential=False):
+        """out[.., r, .., p] = X[.., order[p, r], .., p] for a contiguous [d0, d1, P] tensor; ``sequential`` gives the
+        result of the in-place row-by-row assignment ``for r: X[r] = X[order[p, r]]`` instead (see include/dnmf.h)."""
+        assert X.is_contiguous() and X.dim() == 3 and order.is_contiguous() and order.dtype == torch.int32
+        out = torch.empty_like(X)
+        L.call('dnmf_permute_groups', X.data_ptr(), out.data_ptr(), X.shape[0], X.shape[1], X.shape[2], int(axis),
+               order.data_ptr(), 1 if sequential else 0, _DT[X.dtype], self._stream())
+        return out
+
+    def median_last(self, X, want_mad=False):
+        """np.median(X, axis=-1) (and the median absolute deviation around it) of a contiguous tensor."""
+        assert X.is_contiguous()
+        P = X.shape[-1]
+        rows = X.numel() // max(P, 1)
+        med = self.empty(tuple(X.shape[:-1]), X.dtype)
+        mad = self.empty(tuple(X.shape[:-1]), X.dtype) if want_mad else None
+        L.call('dnmf_median_last', X.data_ptr(), rows, P, med.data_ptr(), mad.data_ptr() if want_mad else 0,
+               _DT[X.dtype], self._stream())
+        return (med, mad) if want_mad else med
+
+    def silhouettes(self, G, k, P):
+        assert G.shape == (k * P, k * P)
+        out = self.empty((k, P), torch.float64)
+        L.call('dnmf_silhouettes', G.data_ptr(), _ld(G), k, P, out.data_ptr(), _DT[G.dtype], self._stream())
+        return out
+
+    # ---- NMFk-level rows: nnsvd initialisation (dist_svd.py) -------------------------------------------
+    def rank1_sub(self, M, u, v, sigma):
+        assert u.dtype == v.dtype == sigma.dtype == torch.float64
+        L.call('dnmf_rank1_sub', M.data_ptr(), _ld(M), M.shape[0], M.shape[1], u.data_ptr(), v.data_ptr(),
+               sigma.data_ptr(), _DT[M.dtype], self._stream())
+        return M
+
+    def matvec_f64(self, A, x, trans=False):
+        """A @ x or A.T @ x with float64 vectors and accumulation (A keeps its dtype in memory)."""
+        assert x.dtype == torch.float64 and x.is_contiguous()
+        r, c = A.shape
+        y = self.empty((c if trans else r,), torch.float64)
+        nb = L.call('dnmf_matvec_workspace_bytes', r, c, 1 if trans else 0)
+        ws = self.workspace(nb)
+        L.call('dnmf_matvec_f64', A.data_ptr(), _ld(A), r, c, x.data_ptr(), y.data_ptr(), 1 if trans else 0,
+               _DT[A.dtype], ws, max(nb, self._ws_bytes), self._stream())
+        return y
+
+    def power_normalize(self, y, v_last, r_out):
+        v = torch.empty_like(y)
+        L.call('dnmf_power_normalize', y.data_ptr(), v_last.data_ptr(), v.data_ptr(), r_out.data_ptr(), y.numel(),
+               self._stream())
+        return v
+
+    def div_store(self, src, sq, dst_col):
+        """dst_col (a strided column view) = src / sqrt(sq)."""
+        L.call('dnmf_div_store', src.data_ptr(), sq.data_ptr(), dst_col.data_ptr(), src.numel(),
+               dst_col.stride(0) if dst_col.numel() > 1 else 1, self._stream())
+
+    def posneg_colsumsq(self, X):
+        r, k = X.shape
+        out = self.empty((2, k), torch.float64)
+        L.call('dnmf_posneg_colsumsq', X.data_ptr(), _ld(X), r, k, out.data_ptr(), self._stream())
+        return out
+
+    def nnsvd_pick(self, X, coef, pos, transpose_out=False):
+        r, k = X.shape
+        out = self.empty((k, r) if transpose_out else (r, k), torch.float64)
+        L.call('dnmf_nnsvd_pick', X.data_ptr(), _ld(X), r, k, coef.data_ptr(), pos.data_ptr(), out.data_ptr(),
+               max(r, 1) if transpose_out else k, 1 if transpose_out else 0, self._stream())
+        return out
+
+    def gram_wide(self, X, chunk=L.MAX_K):
+        """X.T @ X for a tall matrix with any number of columns (the (kP)^2 cosine Gram, the nnsvd d x d Gram):
+        column chunks of X act as the skinny factor of the A-streaming W^T A contraction."""
+        m, c = X.shape
+        G = self.empty((c, c), X.dtype)
+        for c0 in range(0, c, chunk):
+            c1 = min(c0 + chunk, c)
+            self.wta(X, X[:, c0:c1], out=G[c0:c1])
+        return G
+
+    def outer_gram_wide(self, X, Y, chunk=L.MAX_K):
+        """X @ Y.T for wide matrices with few rows (m x m): row chunks of Y act as the skinny factor of A H^T."""
+        m = X.shape[0]
+        r = Y.shape[0]
+        G = self.empty((m, r), X.dtype)
+        for r0 in range(0, r, chunk):
+            r1 = min(r0 + chunk, r)
+            self.ah(X, Y[r0:r1], out=G[:, r0:r1])
+        return G
+
 
 _default_ops = {}
 

@@ -124,9 +124,12 @@ class PyNMF():
             return D.to_device(W, self._tdtype), D.to_device(H, self._tdtype)
         elif self.init == 'nnsvd':
             if self.topo == '1d':
-                raise NotImplementedError(
-                    'nnsvd init (dist_svd.py) is outside the accelerated path (SURVEY section 8f, row N1); '
-                    'pass factors=[W, H] computed by the reference DistSVD, or use init="rand"')
+                # pyDNMF.py:131-134.  The reference keeps DistSVD's float64 factors (numpy then promotes the whole fit
+                # to float64 even for float32 data); the device path casts them to the data dtype like every other
+                # initialisation, parity is asserted at the fp32 tolerance.
+                from .dist_svd import DistSVD
+                W, H = DistSVD(self.params, self.A_ij).nnsvd(flag=1, verbose=0)
+                return W.to(self._tdtype).contiguous(), H.to(self._tdtype).contiguous()
             raise Exception('NNSVD init only available for 1D topology, please try with 1d topo.')
         raise Exception('unknown init: %s' % self.init)
 

@@ -1,10 +1,11 @@
-"""NMFk perturbation ensemble on top of ``PyNMF``.
+"""NMFk: automatic rank estimation from a perturbation ensemble of ``PyNMF`` fits.
 
-Mirrors the hot-path part of ``pyDNMFk/pyDNMFk.py``: ``sample`` (:8-67) and the perturbation loop
-/ result stacking / W-fixed regression fit of ``PyNMFk.pynmfk_per_k`` (:218-248).  Clustering,
-silhouettes, the Wilcoxon rank selection and results.h5 are the "next" rows N2-N4 of SURVEY.md
-section 8f and are not part of this package yet.
+Mirrors ``pyDNMFk/pyDNMFk.py``: ``sample`` (:8-67), ``PyNMFk.fit`` (:169-212), ``pynmfk_per_k`` (:214-258: perturbation
+loop, result stacking, clustering + silhouettes, W-fixed regression fit, per-k results) and ``pvalueAnalysis`` (:261-299).
+The data shard, the ensemble tensors and the clustering stay on the device; only k x P-sized statistics go to the host.
 """
+import os
+
 import numpy as np
 import numpy
 import torch
@@ -66,12 +67,13 @@ class sample():
 
 
 class PyNMFk():
-    r"""Perturbation ensemble for automatic rank estimation (pyDNMFk.py:126-258), ensemble part.
+    r"""Automatic rank estimation (pyDNMFk.py:126-299).
 
-    ``fit_ensemble(k)`` runs ``perturbations`` independent ``PyNMF`` fits of perturbed copies of the
-    resident shard and returns the stacked factors exactly as the reference stacks them before
-    clustering: ``Wall (m_loc, k, P)``, ``Hall (k, n_loc, P)``, ``recon_err [P]``.
-    ``fit_regression(W, H)`` is the W-fixed fit that follows the clustering (pyDNMFk.py:245-248).
+    ``fit()`` sweeps ``k = start_k .. end_k``: per k a perturbation ensemble of ``PyNMF`` fits (``fit_ensemble``),
+    clustering + silhouettes of the stacked factors (``dist_clustering.custom_clustering``), a W-fixed regression fit
+    from the cluster medians (``fit_regression``) and the per-k statistics written under
+    ``results_path/<fname>/<k>/``; then ``pvalueAnalysis`` picks the rank.  ``fit_ensemble`` returns the factors stacked
+    exactly as the reference stacks them: ``Wall (m_loc, k, P)``, ``Hall (k, n_loc, P)``, ``recon_err [P]``.
     """
 
     @comm_timing()
@@ -105,8 +107,9 @@ class PyNMFk():
         self.avgErr = 0
         self.start_time = 0
         self.end_time = 0
-        self.params.checkpoint = var_init(self.params, 'checkpoint', default=False)
+        self.params.checkpoint = var_init(self.params, 'checkpoint', default=True)
         self.params.rank = self.rank
+        self.params.flag = 0      # 1: all perturbations of a k done, 2: clustered, 3: results saved (pyDNMFk.py:165)
         self.cp = Checkpoint(self.params.checkpoint, self.params)
         # keep the shard on the device across all perturbations
         self._A_dev = D.to_device(self.A_ij)
@@ -150,23 +153,30 @@ class PyNMFk():
             saved = self._enter_solo()
         mine = {}
         for perturbation in todo:
+            if self.rank == 0 and self.verbose:
+                print('Current perturbation =', perturbation)
             data = sample(data=self._A_dev, noise_var=self.noise_var, method=self.sampling,
                           seed=perturbation * 1000).fit()
             self.params.W_update = True
             W, H, err = PyNMF(data, factors=None, params=self.params).fit()
-            mine[perturbation] = (W.cpu().numpy(), H.cpu().numpy(), err)
+            mine[perturbation] = (W, H, err)
+            if not spread:
+                self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
         if spread:
             self._leave_solo(saved)
             merged = {}
-            for part in world.allgather(mine):
+            for part in world.allgather({p: (W.cpu().numpy(), H.cpu().numpy(), e) for p, (W, H, e) in mine.items()}):
                 merged.update(part)
-            mine = merged
+            mine = {p: (D.to_device(W), D.to_device(H), e) for p, (W, H, e) in merged.items()}
         results = [mine[p] for p in range(self.perturbations)]
-        self.Wall = np.hstack(([results[i][0] for i in range(self.perturbations)]))
-        self.Wall = self.Wall.reshape(self.Wall.shape[0], self.k, self.perturbations, order='F')
-        self.Hall = np.vstack(([results[i][1] for i in range(self.perturbations)]))
-        self.Hall = self.Hall.reshape(self.k, self.Hall.shape[1], self.perturbations)
-        self.recon_err = [results[i][2] for i in range(self.perturbations)]
+        # Wall[:, :, p] = W_p (hstack + reshape(order='F'), pyDNMFk.py:234-235); Hall is the reference's vstack followed
+        # by a C-order reshape to (k, n, P) (pyDNMFk.py:236-237) -- both kept on the device for the clustering
+        self._Wall_dev = torch.stack([r[0] for r in results], dim=2).contiguous()
+        Hs = torch.cat([r[1] for r in results], dim=0)
+        self._Hall_dev = Hs.reshape(self.k, Hs.shape[1], self.perturbations).contiguous()
+        self.Wall = self._Wall_dev.cpu().numpy()
+        self.Hall = self._Hall_dev.cpu().numpy()
+        self.recon_err = [r[2] for r in results]
         return self.Wall, self.Hall, self.recon_err
 
     def fit_regression(self, AvgW, AvgH):
@@ -182,8 +192,90 @@ class PyNMFk():
         return W.cpu().numpy(), H.cpu().numpy(), err
 
     @comm_timing()
+    def pynmfk_per_k(self):
+        """Ensemble, clustering, silhouettes and the regression fit for ``self.k`` (pyDNMFk.py:214-258)."""
+        from .data_io import data_write
+        from .dist_clustering import custom_clustering
+        self.params.results_paths = self.params.results_path + str(self.k) + '/'
+        if self.rank == 0:
+            os.makedirs(self.params.results_paths, exist_ok=True)
+            if self.verbose:
+                print('*************Computing for k=', self.k, '************')
+        self.fit_ensemble(self.k)
+        perturbation = self.perturbations - 1
+        self.params.flag = 1
+        self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
+        spread = self._spread()
+        saved = self._enter_solo() if spread else None               # replica mode: every rank clusters its full copy
+        clusters = custom_clustering(self._Wall_dev, self._Hall_dev, self.params)
+        [processAvg, processSTD, Hall_dev, self.clusterSilhouetteCoefficients, self.avgSilhouetteCoefficients,
+         idx] = clusters.fit()
+        if saved is not None:
+            self._leave_solo(saved)
+        self._Hall_dev = Hall_dev
+        self.Hall = Hall_dev.cpu().numpy()
+        self.params.flag = 2
+        self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
+        AvgH_dev = D.default_ops().median_last(Hall_dev)              # np.median(self.Hall, axis=-1)
+        self.AvgW, self.AvgH, self.L_errDist = self.fit_regression(processAvg, AvgH_dev)
+        self.avgErr = np.mean(self.recon_err)
+        self.AIC = 2 * self.k + self.params.m * self.params.n * numpy.log(self.avgErr / (self.params.m * self.params.n))
+        cluster_stats = {'clusterSilhouetteCoefficients': self.clusterSilhouetteCoefficients,
+                         'avgSilhouetteCoefficients': self.avgSilhouetteCoefficients, 'L_errDist': self.L_errDist,
+                         'L_err': self.col_err, 'avgErr': self.avgErr, 'recon_err': self.recon_err, 'AIC': self.AIC}
+        if not spread or self.rank == 0:
+            data_writer = data_write(self.params)
+            data_writer.save_factors([self.AvgW, self.AvgH], reg=True)
+            data_writer.save_cluster_results(cluster_stats)
+        self.params.flag = 3
+        self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
+
+    @comm_timing()
+    def pvalueAnalysis(self):
+        """Rank selection from the per-k regression errors and silhouettes (pyDNMFk.py:261-299): walk k upwards and
+        accept k while the previous k clustered stably (min silhouette > sill_thr) and the per-column regression errors
+        dropped significantly (Wilcoxon signed-rank p < 0.05)."""
+        from scipy.stats import wilcoxon
+        from .data_io import read_results
+        k_swap_range = range(self.params.start_k, self.params.end_k + 1, self.step_k)
+        pvalue = np.ones(len(k_swap_range))
+        sill_min, err_regres = [], []
+        for k in k_swap_range:
+            data = read_results(self.params.results_path + str(k) + '/')
+            err_regres.append(np.array(data['L_err']))
+            sill_min.append(round(np.min(np.array(data['clusterSilhouetteCoefficients'])), 2))
+        one_distr_err = err_regres[0]
+        nopt = 1
+        for i in range(1, len(k_swap_range)):
+            if sill_min[i - 1] > self.sill_thr:
+                pvalue[i] = wilcoxon(one_distr_err, err_regres[i])[1]
+                if pvalue[i] < 0.05:
+                    nopt = i
+                    one_distr_err = np.copy(err_regres[i])
+        return k_swap_range[nopt - 1], pvalue
+
+    @comm_timing()
     def fit(self):
-        raise NotImplementedError(
-            'PyNMFk.fit: clustering / silhouettes / p-value rank selection (dist_clustering.py, '
-            'pyDNMFk.py:239-299) are rows N2/N4 of the scope table and not built yet; use '
-            'fit_ensemble(k) and fit_regression(W, H) for the accelerated parts')
+        """NMFk over ``start_k .. end_k``: returns the estimated number of latent features (pyDNMFk.py:169-212)."""
+        self.params.results_path = self.params.results_path + self.params.fname + '/'
+        if self.rank == 0:
+            os.makedirs(self.params.results_path, exist_ok=True)
+        if self.params.checkpoint:
+            try:
+                self.cp.load_from_checkpoint()
+                self.start_k = self.cp.k + self.step_k if self.cp.flag > 3 else self.cp.k
+            except Exception:
+                pass
+        self.comm1.barrier()
+        for self.k in range(self.start_k, self.end_k + 1, self.step_k):
+            self.params.k = self.k
+            self.pynmfk_per_k()
+        self.comm1.barrier()
+        if self.rank == 0:
+            nopt1, pvalue1 = self.pvalueAnalysis()
+            print('Rank estimated by NMFk = ', nopt1)
+        else:
+            nopt1 = None
+        nopt1 = self.comm1.bcast(nopt1, root=0)
+        self.comm1.barrier()
+        return nopt1

@@ -7,6 +7,7 @@ Only the hot-path part of ``pyDNMFk/utils.py`` is mirrored (SURVEY.md section 2 
 host; the per-element work (non-zero counts, compaction, un-prune scatter) runs on the device.
 """
 import copy
+import os
 import pickle
 
 import numpy
@@ -245,6 +246,7 @@ class Checkpoint():
         state = parse()
         state.flag, state.perturbation, state.k = flag, perturbation, k
         if self.checkpoint_save and self.params.rank == 0:
+            os.makedirs(self.params.results_path, exist_ok=True)
             with open(self.params.results_path + "checkpoint.p", "wb") as f:
                 pickle.dump(state, f)
 

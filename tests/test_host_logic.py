@@ -1,4 +1,6 @@
 """Host-side logic that needs no GPU: shard index maps, argument helpers, error messages."""
+import os
+
 import numpy as np
 import pytest
 
@@ -103,3 +105,27 @@ def test_cli_flag_surface():
     a = p.parse_args(['--p_r', '2', '--p_c', '1'])
     assert (a.k, a.itr, a.norm, a.method, a.prune, a.precision, a.init) == (4, 5000, 'kl', 'mu', False, 'float32', 'rand')
     assert (a.perturbations, a.noise_var, a.start_k, a.end_k, a.step_k, a.sill_thr, a.sampling) == (20, 0.015, 1, 10, 1, 0.6, 'uniform')
+
+
+def test_rank_selection_matches_reference():
+    """pvalueAnalysis on fabricated per-k results written through the product's own results store."""
+    import tempfile
+    from oracle import nmfk_cases as K
+    with np.load(os.path.join(K.GOLDEN, 'nmfk_cases.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    from pydnmfk_b200.data_io import write_results
+    from pydnmfk_b200.pyDNMFk import PyNMFk
+    from pydnmfk_b200.utils import parse
+    for name, sc in K.pvalue_scenarios().items():
+        with tempfile.TemporaryDirectory() as tmp:
+            p = parse()
+            p.start_k, p.end_k, p.results_path = sc['start_k'], sc['end_k'], tmp + '/'
+            for i, k in enumerate(range(sc['start_k'], sc['end_k'] + 1, sc['step_k'])):
+                os.makedirs('%s/%d' % (tmp, k))
+                write_results('%s/%d/' % (tmp, k), {'L_err': sc['L_err'][i],
+                                                     'clusterSilhouetteCoefficients': np.array([sc['sil_min'][i], 1.0])})
+            obj = object.__new__(PyNMFk)
+            obj.params, obj.step_k, obj.sill_thr = p, sc['step_k'], sc['sill_thr']
+            nopt, pv = obj.pvalueAnalysis()
+        assert nopt == int(gold['pvalue/%s/0/nopt' % name])
+        assert np.allclose(pv, gold['pvalue/%s/0/pvalue' % name], rtol=1e-12, atol=0)

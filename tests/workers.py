@@ -144,10 +144,130 @@ def ensemble_worker(rank, world, spread):
     p.ensemble_parallel = bool(spread)
     p.comm, p.row_comm, p.col_comm = g, g.cart_1d_row(), g.cart_1d_column()
     p.p_r, p.p_c, p.init, p.verbose, p.itr, p.norm, p.method, p.prune = 1, 1, 'rand', False, 30, 'kl', 'mu', True
-    p.perturbations, p.noise_var, p.sampling = 6, 0.015, 'uniform'
+    p.perturbations, p.noise_var, p.sampling, p.checkpoint = 6, 0.015, 'uniform', False
     nmfk = PyNMFk(A, params=p)
     Wall, Hall, errs = nmfk.fit_ensemble(3)
     AvgW, AvgH = Wall[:, :, 0], np.median(Hall, axis=-1)
     Wr, Hr, er = nmfk.fit_regression(AvgW, AvgH)
     return dict(Wall=Wall, Hall=Hall, errs=[float(e) for e in errs], Wr=Wr, Hr=Hr, er=float(er),
                 col_err=np.asarray(nmfk.col_err))
+
+
+# ---- NMFk-level rows (clustering, nnsvd, end to end) ---------------------------------------------------------------
+def _grid_params(rank, world, p_r, p_c):
+    import torch
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm
+    from pydnmfk_b200.utils import parse
+    torch.cuda.set_device(0)
+    comm = MPI.COMM_WORLD
+    comms = MPI_comm(comm, p_r, p_c)
+    p = parse()
+    p.size, p.rank, p.comm1, p.comm, p.p_r, p.p_c = world, rank, comms.comm, comms, p_r, p_c
+    p.row_comm, p.col_comm = comms.cart_1d_row(), comms.cart_1d_column()
+    return p
+
+
+def _guarded(fn, cases, *a):
+    """Run fn(case) for a batch of cases in one process group; stop the batch on every rank together on a failure."""
+    import traceback
+    from pydnmfk_b200.dist_comm import MPI
+    out = {}
+    for case in cases:
+        try:
+            out[case['name']] = ('ok', fn(case, *a))
+            ok = 1
+        except BaseException:
+            out[case['name']] = ('err', traceback.format_exc())
+            ok = 0
+        if MPI.COMM_WORLD.allreduce(ok) != MPI.COMM_WORLD.size:
+            break
+    return out
+
+
+def cluster_worker(rank, world, cases):
+    from oracle import nmfk_cases as K
+    from pydnmfk_b200.dist_clustering import custom_clustering
+
+    def one(case):
+        W_all, H_all = K.cluster_inputs(case)
+        s, e = K.row_split(case['m'], case['p_r'])[rank]
+        p = _grid_params(rank, world, case['p_r'], 1)
+        p.eps = np.finfo(W_all.dtype).eps
+        cl = custom_clustering(np.ascontiguousarray(W_all[s:e]), H_all.copy(), p)
+        centroids, cent_std, H_out, sil_k, sil_avg, order = cl.fit()
+        return dict(centroids=centroids, cent_std=cent_std, H_all=H_out, W_all=cl.W_all, sil_k=sil_k,
+                    sil_avg=float(sil_avg), order=np.asarray(order, dtype=np.int64), sils=cl.dist_silhouettes())
+    return _guarded(one, cases)
+
+
+def _block_of(A, rank, grid):
+    from pydnmfk_b200.utils import determine_block_params
+    b = determine_block_params(rank, grid, A.shape).determine_block_index_range_asymm()
+    return np.ascontiguousarray(A[b[0][0]:b[1][0] + 1, b[0][1]:b[1][1] + 1])
+
+
+def nnsvd_worker(rank, world, cases):
+    import random
+    from oracle import nmfk_cases as K
+    from pydnmfk_b200.dist_svd import DistSVD
+
+    def one(case):
+        A = K.nnsvd_input(case)
+        p_r, p_c = case['grid']
+        p = _grid_params(rank, world, p_r, p_c)
+        p.m, p.n, p.k = case['m'], case['n'], case['k']
+        p.eps = np.finfo(A.dtype).eps
+        random.seed(K.NNSVD_PY_SEED)
+        (W, H), err = DistSVD(p, _block_of(A, rank, (p_r, p_c))).nnsvd(flag=1, verbose=1)
+        return dict(W=W, H=H, err_svd=float(err['recon_err_svd']), err_nnsvd=float(err['recon_err_nnsvd']))
+    return _guarded(one, cases)
+
+
+def nnsvd_fit_worker(rank, world, cases):
+    import random
+    from oracle import nmfk_cases as K
+    from pydnmfk_b200.pyDNMF import PyNMF
+
+    def one(case):
+        A = K.nnsvd_fit_input(case)
+        p_r, p_c = case['grid']
+        p = _grid_params(rank, world, p_r, p_c)
+        p.m, p.n, p.k = case['m'], case['n'], case['k']
+        p.itr, p.init, p.verbose, p.norm, p.method = case['itr'], 'nnsvd', False, case['norm'], case['method']
+        random.seed(K.NNSVD_PY_SEED)
+        W, H, err = PyNMF(_block_of(A, rank, (p_r, p_c)), factors=None, params=p).fit()
+        return dict(W=np.asarray(W), H=np.asarray(H), err=float(err))
+    return _guarded(one, cases)
+
+
+def nmfk_e2e_worker(rank, world, case, tmp):
+    """PyNMFk.fit() on the 96 x 21 example matrix; returns nopt and the per-k results this rank wrote."""
+    import random
+    from oracle import nmfk_cases as K
+    from pydnmfk_b200.data_io import read_results
+    from pydnmfk_b200.pyDNMFk import PyNMFk
+    X = K.wtsi().astype('float32')
+    p_r, p_c = case['grid']
+    p = _grid_params(rank, world, p_r, p_c)
+    p.fpath, p.fname, p.ftype = 'data/', 'wtsi', 'mat'
+    p.init, p.itr, p.norm, p.method, p.verbose = case['init'], case['itr'], case['norm'], case['method'], False
+    p.start_k, p.end_k, p.step_k, p.sill_thr = case['start_k'], case['end_k'], 1, case['sill_thr']
+    p.perturbations, p.noise_var, p.sampling = case['perturbations'], case['noise_var'], 'uniform'
+    p.results_path, p.checkpoint, p.precision = tmp + '/', False, 'float32'
+    random.seed(K.NNSVD_PY_SEED)
+    nopt = PyNMFk(_block_of(X, rank, (p_r, p_c)), factors=None, params=p).fit()
+    out = dict(nopt=int(nopt))
+    for k in range(case['start_k'], case['end_k'] + 1):
+        d = '%s/wtsi/%d/' % (tmp, k)
+        if rank == 0:
+            for key, val in read_results(d).items():
+                out['k%d/%s' % (k, key)] = np.asarray(val, dtype=np.float64)
+        if p_r == 1 and p_c == 1:
+            wname, hname = 'W_reg_factors/W_0.npy', 'H_reg_factors/H_0.npy'
+        elif p_c == 1:
+            wname, hname = 'W_reg_factors/W_%d.npy' % rank, 'H_reg_factors/H.npy'
+        else:
+            wname, hname = 'W_reg_factors/W.npy', 'H_reg_factors/H_%d.npy' % rank
+        out['k%d/W_reg' % k] = np.load(d + wname)
+        out['k%d/H_reg' % k] = np.load(d + hname)
+    return out

@@ -88,20 +88,25 @@ if 'cfg4' in only:
     torch.cuda.empty_cache()
 
 if 'cfg5' in only:
-    rs = np.random.RandomState(5)
-    A = (rs.rand(96, 21) * 100).astype(np.float32)
-    p = params(2, 'kl', 'mu', 1000, 96, 21)
-    p.perturbations, p.noise_var, p.sampling, p.prune = 20, 0.015, 'uniform', True
-    nk = PyNMFk(A, params=p)
-    nk.fit_ensemble(2)                                # warm-up
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    fits = 0
-    for k in range(2, 11):
-        nk.fit_ensemble(k)
-        fits += p.perturbations
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print(json.dumps({'config': 'cfg5: 96x21 fp32, k=2..10, 20 perturbations, KL-MU itr=1000, rand init, 1 GPU (sequential fits)',
-                      'ensemble_wall_s': dt, 'fits': fits, 'ms_per_fit': dt / fits * 1e3,
-                      'us_per_iteration': dt / fits / 1000 * 1e6}), flush=True)
+    import tempfile
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+    from oracle import nmfk_cases as K      # the 96 x 21 example matrix fixture only (no oracle compute)
+    A = K.wtsi().astype(np.float32)
+    with tempfile.TemporaryDirectory() as tmp:
+        def nmfk(end_k, itr):
+            p = params(2, 'kl', 'mu', itr, 96, 21)
+            p.perturbations, p.noise_var, p.sampling, p.prune, p.checkpoint = 20, 0.015, 'uniform', True, False
+            p.start_k, p.end_k, p.step_k, p.sill_thr, p.fname = 2, end_k, 1, 0.9, 'wtsi_%d_%d' % (end_k, itr)
+            p.results_path = tmp + '/'
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nopt = PyNMFk(A, params=p).fit()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, nopt
+        nmfk(2, 50)                                        # warm-up
+        dt, nopt = nmfk(10, 1000)
+    fits = 9 * 20
+    print(json.dumps({'config': 'cfg5: wtsi 96x21 fp32, PyNMFk.fit k=2..10, 20 perturbations, KL-MU itr=1000, rand init, '
+                                'sill_thr 0.9, 1 GPU (ensemble + clustering + silhouettes + regression + rank selection)',
+                      'nmfk_wall_s': dt, 'nopt': int(nopt), 'perturbation_fits': fits, 'ms_per_fit_incl_clustering': dt / fits * 1e3}),
+          flush=True)
