@@ -21,11 +21,12 @@ namespace dnmf {
 
 template <typename T, int KP, bool KL>
 Split row_pass_plan(int64_t m, int64_t n) {
-  return plan_split(m, RowPassCfg<T, KP, KL>::BM, n, kRowPassBK, 8 * kRowPassBK);
+  // (min chunk of 2 K-tiles: mid-sized shards such as 1024 x 256 still spread over many CTAs)
+  return plan_split(m, RowPassCfg<T, KP, KL>::BM, n, kRowPassBK, 2 * kRowPassBK);
 }
 template <typename T, int KP, bool KL>
 Split col_pass_plan(int64_t m, int64_t n) {
-  return plan_split(n, (int64_t)kColPassThreads * ColPassCfg<T, KP, KL>::CPT, m, kColPassBR, 4 * kColPassBR);
+  return plan_split(n, (int64_t)kColPassThreads * ColPassCfg<T, KP, KL>::CPT, m, kColPassBR, kColPassBR);
 }
 
 template <typename T>

@@ -452,6 +452,28 @@ class DeviceOps:
             self.ah(X, Y[r0:r1], out=G[:, r0:r1])
         return G
 
+    # ---- whole-fit on-chip MU (tiny shards; the batch is the NMFk perturbation ensemble) ---------------------
+    @staticmethod
+    def resident_fit_fits(m, n, k, norm, dtype):
+        """True when one (m x n, k) MU fit fits in an SM's shared memory (dnmf_mu_fit_resident)."""
+        if norm.lower() not in ('fro', 'kl') or dtype not in _DT:
+            return False
+        return L.call('dnmf_mu_fit_resident_smem_bytes', int(m), int(n), int(k), 1 if norm.lower() == 'kl' else 0, _DT[dtype]) > 0
+
+    def mu_fit_resident(self, As, Ws, Hs, norm, w_update, it_begin, it_end, eps):
+        """Iterations [it_begin, it_end) of the MU loop (+ every-10th clamp) for len(As) independent fits in one launch;
+        W and H are updated in place."""
+        m, n = As[0].shape
+        k = Ws[0].shape[1]
+        for A, W, H in zip(As, Ws, Hs):
+            assert A.shape == (m, n) and W.shape == (m, k) and H.shape == (k, n) and A.dtype == W.dtype == H.dtype
+            assert W.is_contiguous() and H.is_contiguous() and _ld(A) == _ld(As[0])
+        ptrs = torch.tensor([[t.data_ptr() for t in grp] for grp in (As, Ws, Hs)], dtype=torch.int64).to(self.device)
+        L.call('dnmf_mu_fit_resident', ptrs[0].data_ptr(), _ld(As[0]), ptrs[1].data_ptr(), ptrs[2].data_ptr(), len(As),
+               m, n, k, 1 if norm.lower() == 'kl' else 0, 1 if w_update else 0, int(it_begin), int(it_end), float(eps),
+               _DT[As[0].dtype], self._stream())
+        self._keep = ptrs          # the pointer table must outlive the asynchronous launch
+
 
 _default_ops = {}
 

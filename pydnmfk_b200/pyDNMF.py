@@ -140,14 +140,23 @@ class PyNMF():
         t = D.to_device(X if X is not None else np.empty(shape, dtype=self._np_dtype), self._tdtype)
         return self.comm1.bcast_(t, root=0)
 
-    @comm_timing()
-    def fit(self):
-        r"""Run ``itr`` update steps; returns ``(W, H, recon_err)`` as host arrays (W, H in the data
-        dtype, or float64 after un-pruning -- utils.py:195,198) and a numpy scalar."""
+    def _resident_ok(self):
+        """Whole-fit on-chip path (dnmf_mu_fit_resident): single-process grid, MU, shard + factors fit in one SM."""
         W, H = self._get_factors()
+        return (self.comm1.size == 1 and self.method.lower() == 'mu' and self.norm.lower() in ('fro', 'kl')
+                and var_init(self.params, 'resident_fit', True) and self.itr >= 1 and W.shape[0] > 0 and H.shape[1] > 0
+                and self.ops.resident_fit_fits(W.shape[0], H.shape[1], self.k, self.norm, self._tdtype))
+
+    def _run_loop(self):
+        """The ``itr`` update steps of pyDNMF.py:151-172 (update + every-10th clamp) on the resident factors."""
+        W, H = self._get_factors()
+        if self._resident_ok():
+            self.ops.mu_fit_resident([self.A_ij], [W], [H], self.norm, self.params.W_update, 0, self.itr, self.eps)
+            return
         Alg = nmf_algorithms_2D if self.topo == '2d' else nmf_algorithms_1D
         alg = Alg(self.A_ij, W, H, params=self.params)
         self._alg = alg
+
         def clamp():                                                    # pyDNMF.py:155-157 / :170-172
             self.ops.clamp_min(H, self.eps)
             self.ops.clamp_min(W, self.eps)
@@ -169,20 +178,37 @@ class PyNMF():
                 if i % 10 == 0:
                     clamp()
             if i == self.itr - 1:
-                W, H = self.normalize_features(W, H)
-                self._set_factors(W, H)
-                self.relative_err()
-                if self.verbose == True:  # noqa: E712
-                    if self.rank == 0:
-                        print('relative error is:', self.recon_err)
-                if self.save_factors:
-                    data_write(self.params).save_factors([W.cpu().numpy(), H.cpu().numpy()])  # noqa: F405
-                sg = None                      # drop the captured graphs (and their NCCL nodes) with the fit
-                if self.topo == '2d':
-                    self.comm.Free()
-                if self.prune:
-                    W, H = self.data_op.unprune_factors(W, H)
-                return self._to_host(W), self._to_host(H), self.recon_err
+                break
+        sg = None                              # drop the captured graphs (and their NCCL nodes) with the loop
+
+    def _finish(self):
+        """What the reference does on the last iteration (pyDNMF.py:158-166,173-181): normalise, relative error,
+        optional save, un-prune; returns ``(W, H, recon_err)``."""
+        W, H = self._get_factors()
+        W, H = self.normalize_features(W, H)
+        self._set_factors(W, H)
+        if self.topo == '2d' and not hasattr(self, '_alg'):
+            self._alg = nmf_algorithms_2D(self.A_ij, W, H, params=self.params)
+        self.relative_err()
+        if self.verbose == True:  # noqa: E712
+            if self.rank == 0:
+                print('relative error is:', self.recon_err)
+        if self.save_factors:
+            data_write(self.params).save_factors([W.cpu().numpy(), H.cpu().numpy()])  # noqa: F405
+        if self.topo == '2d':
+            self.comm.Free()
+        if self.prune:
+            W, H = self.data_op.unprune_factors(W, H)
+        return self._to_host(W), self._to_host(H), self.recon_err
+
+    @comm_timing()
+    def fit(self):
+        r"""Run ``itr`` update steps; returns ``(W, H, recon_err)`` as host arrays (W, H in the data
+        dtype, or float64 after un-pruning -- utils.py:195,198) and a numpy scalar."""
+        if self.itr < 1:
+            return None
+        self._run_loop()
+        return self._finish()
 
     def _to_host(self, t):
         return t.cpu().numpy() if self._numpy_in else t

@@ -152,16 +152,36 @@ class PyNMFk():
             todo = todo[world.rank::world.size]
             saved = self._enter_solo()
         mine = {}
+        pending = []
         for perturbation in todo:
             if self.rank == 0 and self.verbose:
                 print('Current perturbation =', perturbation)
             data = sample(data=self._A_dev, noise_var=self.noise_var, method=self.sampling,
                           seed=perturbation * 1000).fit()
             self.params.W_update = True
-            W, H, err = PyNMF(data, factors=None, params=self.params).fit()
-            mine[perturbation] = (W, H, err)
+            fit = PyNMF(data, factors=None, params=self.params)
+            if self.sampling == 'uniform' and fit._resident_ok():
+                # tiny shard: the update loops of all perturbations run as ONE launch, one CTA per fit (the
+                # perturbations share A's zero pattern, hence the pruned shapes and the masks left on params)
+                pending.append((perturbation, fit))
+                continue
+            mine[perturbation] = fit.fit()
             if not spread:
                 self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
+        if pending:
+            fits = [f for _, f in pending]
+            shapes = {(tuple(f.A_ij.shape), f.A_ij.stride(0)) for f in fits}
+            if len(shapes) == 1:
+                D.default_ops().mu_fit_resident([f.A_ij for f in fits], [f._get_factors()[0] for f in fits],
+                                                [f._get_factors()[1] for f in fits], fits[0].norm, True, 0, fits[0].itr,
+                                                fits[0].eps)
+            else:
+                for f in fits:
+                    f._run_loop()
+            for perturbation, f in pending:
+                mine[perturbation] = f._finish()
+                if not spread:
+                    self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
         if spread:
             self._leave_solo(saved)
             merged = {}

@@ -232,3 +232,67 @@ def test_errors(ops):
     H = torch.zeros((65, 8), device='cuda')
     with pytest.raises(L.DnmfError, match='DNMF_MAX_K'):
         ops.ah(A, H)
+
+
+# ---- whole-fit on-chip multiplicative updates (dnmf_mu_fit_resident) --------------------------------------------
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('norm', ['fro', 'kl'])
+@pytest.mark.parametrize('m,n,k', [(96, 21, 4), (40, 64, 7), (130, 33, 1), (17, 200, 16), (64, 48, 64)])
+def test_resident_fit_equals_per_kernel_loop(dtype, norm, m, n, k):
+    """The on-chip loop follows the per-kernel update + clamp sequence (same math, different summation order)."""
+    import torch
+    from pydnmfk_b200 import device as D
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm
+    from pydnmfk_b200.dist_nmf import nmf_algorithms_1D
+    from pydnmfk_b200.utils import parse
+    ops = D.default_ops()
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    if not ops.resident_fit_fits(m, n, k, norm, tdt):
+        pytest.skip('does not fit in shared memory')
+    MPI._reset()
+    comm = MPI.COMM_WORLD
+    comms = MPI_comm(comm, 1, 1)
+    rs = np.random.RandomState(m + n + k)
+    eps = float(np.finfo(dtype).eps)
+    B = 3
+    A = [rs.rand(m, n).astype(dtype) for _ in range(B)]
+    A[0][rs.rand(m, n) < 0.3] = 0
+    W0 = [rs.rand(m, k).astype(dtype) for _ in range(B)]
+    H0 = [rs.rand(k, n).astype(dtype) for _ in range(B)]
+    dev = lambda x: torch.from_numpy(x.copy()).cuda()     # noqa: E731
+    for w_update in (True, False):
+        itr = 23
+        ref = []
+        for b in range(B):
+            p = parse()
+            p.m, p.n, p.p_r, p.p_c, p.k, p.comm1, p.norm, p.method = m, n, 1, 1, k, comm, norm, 'mu'
+            p.row_comm, p.col_comm = comms.cart_1d_row(), comms.cart_1d_column()
+            p.eps, p.W_update, p.itr = np.finfo(dtype).eps, w_update, itr
+            Ad, Wd, Hd = dev(A[b]), dev(W0[b]), dev(H0[b])
+            alg = nmf_algorithms_1D(Ad, Wd, Hd, params=p)
+            for i in range(itr):
+                alg.update()
+                if i % 10 == 0:
+                    ops.clamp_min(Hd, eps)
+                    ops.clamp_min(Wd, eps)
+            ref.append((Wd.cpu().numpy(), Hd.cpu().numpy()))
+        As, Ws, Hs = [dev(a) for a in A], [dev(w) for w in W0], [dev(h) for h in H0]
+        ops.mu_fit_resident(As, Ws, Hs, norm, w_update, 0, 9, eps)      # split ranges: the clamp phase follows `it`
+        ops.mu_fit_resident(As, Ws, Hs, norm, w_update, 9, itr, eps)
+        torch.cuda.synchronize()
+        tol = 2e-4 if dtype == np.float32 else 1e-11
+        for b in range(B):
+            dW, dH = T.rel_fro(Ws[b].cpu().numpy(), ref[b][0]), T.rel_fro(Hs[b].cpu().numpy(), ref[b][1])
+            assert dW <= tol and dH <= tol, (w_update, b, dW, dH)
+            if not w_update:
+                assert np.array_equal(Ws[b].cpu().numpy()[W0[b] > eps], W0[b][W0[b] > eps])
+
+
+def test_resident_fit_limits():
+    import torch
+    from pydnmfk_b200 import device as D
+    ops = D.default_ops()
+    assert ops.resident_fit_fits(96, 21, 10, 'kl', torch.float32)
+    assert not ops.resident_fit_fits(1024, 256, 4, 'kl', torch.float32)       # 1 MiB shard + U: more than one SM holds
+    assert not ops.resident_fit_fits(96, 21, 65, 'fro', torch.float32)
+    assert not ops.resident_fit_fits(96, 21, 4, 'l1', torch.float32)

@@ -68,13 +68,13 @@ def _compare(case, res):
             '%s rank %d: err %.9g vs %.9g' % (case['name'], r, o['err'], ge)
 
 
-def _run(case, force_generic=False):
+def _run(case, force_generic=False, resident=True):
     world = case['grid'][0] * case['grid'][1]
     if world == 1:
         from pydnmfk_b200.dist_comm import MPI
         MPI._reset()
-        return [workers.fit_worker(0, 1, case, force_generic)]
-    return mp_util.run(world, workers.fit_worker, (case, force_generic), backend='gloo', timeout=900)
+        return [workers.fit_worker(0, 1, case, force_generic, resident)]
+    return mp_util.run(world, workers.fit_worker, (case, force_generic, resident), backend='gloo', timeout=900)
 
 
 SINGLE = [c for c in C.CASES if c['grid'] == (1, 1)]
@@ -86,7 +86,18 @@ MULTI_PICK = [c for c in MULTI_PICK if not (c['name'].startswith('u64x48k4') and
 
 @pytest.mark.parametrize('case', SINGLE, ids=[c['name'] for c in SINGLE])
 def test_single_rank_matches_reference(case):
-    _compare(case, _run(case))
+    """Per-kernel path (CUDA-graph replay of the update step)."""
+    _compare(case, _run(case, resident=False))
+
+
+SINGLE_MU = [c for c in SINGLE if c['method'] == 'mu']
+
+
+@pytest.mark.parametrize('case', SINGLE_MU, ids=[c['name'] for c in SINGLE_MU])
+def test_single_rank_resident_fit_matches_reference(case):
+    """Whole-fit on-chip kernel (dnmf_mu_fit_resident) for shards that fit in one SM's shared memory; larger ones fall
+    through to the per-kernel path."""
+    _compare(case, _run(case, resident=True))
 
 
 _multi_cache = {}

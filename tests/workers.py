@@ -69,8 +69,9 @@ def dims_worker(rank, world, case):
     return dict(geom=[int(v) for v in geom], W=W, H=H)
 
 
-def fit_worker(rank, world, case, force_generic=False):
-    """One PyNMF.fit of a parity case on this rank (GPU; several ranks may share cuda:0 via gloo)."""
+def fit_worker(rank, world, case, force_generic=False, resident=True):
+    """One PyNMF.fit of a parity case on this rank (GPU; several ranks may share cuda:0 via gloo).  ``resident=False``
+    keeps tiny single-rank fits on the per-kernel path instead of the whole-fit on-chip kernel."""
     import torch
     from oracle import cases as C
     from pydnmfk_b200 import _lib as L
@@ -91,6 +92,7 @@ def fit_worker(rank, world, case, force_generic=False):
     args.row_comm, args.col_comm = comms.cart_1d_row(), comms.cart_1d_column()
     args.norm, args.method, args.prune = case['norm'], case['method'], case['prune']
     args.W_update = case['W_update']
+    args.resident_fit = resident
     blk = determine_block_params(rank, (p_r, p_c), A.shape).determine_block_index_range_asymm()
     A_ij = np.ascontiguousarray(A[blk[0][0]:blk[1][0] + 1, blk[0][1]:blk[1][1] + 1])
     factors = None
