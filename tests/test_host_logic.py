@@ -129,3 +129,58 @@ def test_rank_selection_matches_reference():
             nopt, pv = obj.pvalueAnalysis()
         assert nopt == int(gold['pvalue/%s/0/nopt' % name])
         assert np.allclose(pv, gold['pvalue/%s/0/pvalue' % name], rtol=1e-12, atol=0)
+
+
+def test_data_io_formats(tmp_path):
+    """Shard input formats (data_io.py:12-105) and the per-k results / factor files (data_io.py:139-261), host only."""
+    import scipy.io
+    from pydnmfk_b200.data_io import data_read, data_write, read_factors, read_results, write_results
+    from pydnmfk_b200.utils import parse
+
+    class _Comm:
+        def __init__(self, rank):
+            self.rank = rank
+
+        def barrier(self):
+            pass
+
+    rs = np.random.RandomState(0)
+    X = rs.rand(26, 14)
+    d = str(tmp_path) + '/'
+    np.save(d + 'X.npy', X)
+    np.savetxt(d + 'X.csv', X, delimiter=',')
+    scipy.io.savemat(d + 'X.mat', {'X': X})
+    for rank in range(4):
+        s, e = O.block_range(rank, (2, 2), X.shape)
+        np.save(d + 'A_%d.npy' % rank, X[s[0]:e[0] + 1, s[1]:e[1] + 1])
+    for ftype, fname in (('npy', 'X'), ('csv', 'X'), ('mat', 'X'), ('folder', 'A_')):
+        for rank in range(4):
+            p = parse()
+            p.fpath, p.fname, p.ftype, p.p_r, p.p_c, p.comm1, p.precision = d, fname, ftype, 2, 2, _Comm(rank), 'float32'
+            got = data_read(p).read()
+            s, e = O.block_range(rank, (2, 2), X.shape)
+            assert got.dtype == np.float32 and got.flags.c_contiguous
+            assert np.allclose(got, X[s[0]:e[0] + 1, s[1]:e[1] + 1].astype(np.float32), rtol=1e-6), (ftype, rank)
+    # regression factors of a 2 x 2 grid: W blocks stack by rank, H blocks are ordered (j, i) (SURVEY A2)
+    W = rs.rand(26, 3)
+    H = rs.rand(3, 14)
+    for rank in range(4):
+        i, j = divmod(rank, 2)
+        p = parse()
+        p.p_r, p.p_c, p.comm1, p.results_paths, p.ftype = 2, 2, _Comm(rank), d + 'res/', 'npy'
+        (r0, _), (r1, _) = O.block_range(rank, (4, 1), (26, 3))           # W rows: rank order
+        hb = j * 2 + i                                                  # H columns: (j, i) order
+        (_, c0), (_, c1) = O.block_range(hb, (1, 4), (3, 14))
+        data_write(p).save_factors([W[r0:r1 + 1], H[:, c0:c1 + 1]], reg=True)
+    Wr, Hr = read_factors(d + 'res/', (2, 2)).load_factors()
+    assert np.array_equal(Wr, W) and np.array_equal(Hr, H)
+    stats = {'clusterSilhouetteCoefficients': np.array([0.9, 0.8]), 'avgSilhouetteCoefficients': 0.85, 'L_err': rs.rand(14),
+             'L_errDist': 0.1, 'avgErr': 0.2, 'recon_err': [0.2, 0.21], 'AIC': -3.0}
+    p = parse()
+    p.p_r, p.p_c, p.comm1, p.results_paths, p.ftype = 1, 1, _Comm(0), d + 'res/', 'npy'
+    data_write(p).save_cluster_results(stats)
+    back = read_results(d + 'res/')
+    assert set(back) == {'clusterSilhouetteCoefficients', 'avgSilhouetteCoefficients', 'L_err', 'L_errDist', 'avgErr', 'ErrTol', 'AIC'}
+    assert np.array_equal(back['L_err'], stats['L_err']) and np.array_equal(back['ErrTol'], np.array(stats['recon_err']))
+    write_results(d + 'res/', {'L_err': np.arange(3.0)})
+    assert np.array_equal(read_results(d + 'res/')['L_err'], np.arange(3.0))

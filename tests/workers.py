@@ -273,3 +273,78 @@ def nmfk_e2e_worker(rank, world, case, tmp):
         out['k%d/W_reg' % k] = np.load(d + wname)
         out['k%d/H_reg' % k] = np.load(d + hname)
     return out
+
+
+def reference_suite_worker(rank, world):
+    """The reference's own MPI tests (tests/test_dist_nmf_1d.py, test_dist_nmf_2d.py, test_dist_nmf_1d_nnsvd_init.py,
+    test_dist_utils.py), restated against the `pyDNMFk` import alias with the reference's thresholds, on 2 ranks."""
+    import random
+    import torch
+    torch.cuda.set_device(0)
+    ns = {}
+    exec('import pyDNMFk.config as config\nconfig.init(0)\nfrom pyDNMFk.pyDNMF import *\nfrom pyDNMFk.dist_comm import *', ns)
+    np_, MPI, MPI_comm, parse, PyNMF = ns['np'], ns['MPI'], ns['MPI_comm'], ns['parse'], ns['PyNMF']
+    determine_block_params, data_operations = ns['determine_block_params'], ns['data_operations']
+    comm = MPI.COMM_WORLD
+    out = {}
+
+    def run_grid(A, grid, k, itr, init, combos):
+        p_r, p_c = grid
+        comms = MPI_comm(comm, p_r, p_c)
+        args = parse()
+        args.size, args.rank, args.comm1, args.comm, args.p_r, args.p_c = comm.size, comm.rank, comms.comm, comms, p_r, p_c
+        args.m, args.n, args.k = A.shape[0], A.shape[1], k
+        args.itr, args.init = itr, init
+        args.row_comm, args.col_comm = comms.cart_1d_row(), comms.cart_1d_column()
+        args.verbose = False
+        b = determine_block_params(comm.rank, (p_r, p_c), A.shape).determine_block_index_range_asymm()
+        A_ij = np_.ascontiguousarray(A[b[0][0]:b[1][0] + 1, b[0][1]:b[1][1] + 1])
+        errs = {}
+        for mthd, norm in combos:
+            args.method, args.norm = mthd, norm
+            W_ij, H_ij, rel_error = PyNMF(A_ij, factors=None, params=args).fit()
+            errs['%s_%s' % (norm, mthd)] = float(rel_error)
+        return errs
+
+    combos = [('mu', 'fro'), ('mu', 'kl'), ('bcd', 'fro'), ('hals', 'fro')]
+    # tests/test_dist_nmf_1d.py:11-39 (threshold 1e-3) and test_dist_nmf_2d.py (same recipe, threshold 1e-4 on [2, 1])
+    np_.random.seed(100)
+    m, k, n = 24, 2, 12
+    A = np_.random.rand(m, k) @ np_.random.rand(k, n)
+    for grid in ([1, 2], [2, 1]):
+        out['nmf_%dx%d' % tuple(grid)] = run_grid(A, grid, k, 2000, 'rand', combos)
+    # tests/test_dist_nmf_2d.py:11-40: the same recipe, freshly seeded, grid [2, 1] only, threshold 1e-4
+    np_.random.seed(100)
+    A = np_.random.rand(m, k) @ np_.random.rand(k, n)
+    out['nmf2d_2x1'] = run_grid(A, [2, 1], k, 2000, 'rand', combos)
+    # tests/test_dist_nmf_1d_nnsvd_init.py:12-40 (threshold 1e-1)
+    np_.random.seed(100)
+    random.seed(7)
+    for grid, (mm, nn) in zip([[2, 1], [1, 2]], [(24, 12), (12, 24)]):
+        A = np_.random.rand(mm, 2) @ np_.random.rand(2, nn)
+        out['nnsvd_%dx%d' % tuple(grid)] = run_grid(A, grid, 2, 2000, 'nnsvd', combos)
+    # tests/test_dist_utils.py:10-51: prune / un-prune keeps the factor shapes (wtsi with 3 zero rows / columns added)
+    from oracle import nmfk_cases as K
+    for grid in ([1, 2], [2, 1]):
+        A = K.wtsi().astype(np_.float64)
+        z_c = np_.zeros((A.shape[0], 1))
+        A = np_.hstack((z_c, A[:, :A.shape[1] // 2], z_c, A[:, A.shape[1] // 2:], z_c))
+        z_r = np_.zeros((1, A.shape[1]))
+        A = np_.vstack((z_r, A[:A.shape[0] // 2, :], z_r, A[A.shape[0] // 2:, :], z_r))
+        args = parse()
+        comms = MPI_comm(comm, grid[0], grid[1])
+        args.topo = '1d'
+        args.size, args.rank, args.comm, args.p_r, args.p_c = comms.size, comms.rank, comms, grid[0], grid[1]
+        args.row_comm, args.col_comm, args.comm1 = comms.cart_1d_row(), comms.cart_1d_column(), comms.comm
+        args.k = 4
+        b = determine_block_params(comms.rank, (grid[0], grid[1]), A.shape).determine_block_index_range_asymm()
+        A_ij = np_.ascontiguousarray(A[b[0][0]:b[1][0] + 1, b[0][1]:b[1][1] + 1])
+        data_op = data_operations(A_ij, args)
+        data_op.zero_idx_prune()
+        W_i_ = np_.random.rand(data_op.params.m_loc, args.k)
+        H_j_ = np_.random.rand(args.k, data_op.params.n_loc)
+        A_p, W_i, H_j = data_op.prune_all(W_i_, H_j_)
+        W_u, H_u = data_op.unprune_factors(W_i, H_j)
+        out['prune_%dx%d' % tuple(grid)] = dict(orig=(W_i_.shape, H_j_.shape), pruned=(tuple(A_p.shape), tuple(W_i.shape), tuple(H_j.shape)),
+                                                unpruned=(tuple(W_u.shape), tuple(H_u.shape)))
+    return out
