@@ -242,16 +242,20 @@ int dnmf_posneg_colsumsq(const double* X, int64_t ldx, int64_t rows, int64_t k, 
 int dnmf_nnsvd_pick(const double* X, int64_t ldx, int64_t rows, int64_t k, const double* coef, const int32_t* pos,
                     double* out, int64_t ldo, int transpose_out, void* stream);
 
-/* ---- whole-fit on-chip multiplicative updates for shards that fit in one SM's shared memory --------------------
- * dnmf_mu_fit_resident: `batch` independent fits, one CTA each, ONE launch: A_b, W_b, H_b (device arrays of `batch`
+/* ---- whole-fit on-chip multiplicative updates for shards that fit in shared memory ------------------------------
+ * dnmf_mu_fit_resident: `batch` independent fits in ONE launch, each on one CTA (shards up to ~200 KB) or on a
+ *   thread-block cluster of 2..16 CTAs (shards of a few MB: row blocks of A and W per CTA, H replicated, the
+ *   W^T A / W^T W partials summed through distributed shared memory).  A_b, W_b, H_b (device arrays of `batch`
  *   device pointers; A_b [m x n] with leading dimension lda, W_b [m x k], H_b [k x n] contiguous) are loaded into
  *   shared memory and iterations i = it_begin .. it_end-1 of PyNMF.fit's loop body run on chip:
  *   update() (kl = 0: dist_nmf.py:715-771 FRO-MU, kl = 1: :803-869 KL-MU; W half-step only if w_update) followed by
  *   the clamp max(., eps) when i % 10 == 0 (pyDNMF.py:151-157,168-172).  The batch is the NMFk perturbation
  *   ensemble (pyDNMFk.py:226-233).  Single-process grids only (no collectives inside).
- * dnmf_mu_fit_resident_smem_bytes: shared memory one fit needs, or -1 if it does not fit / is not supported.
+ * dnmf_mu_fit_resident_smem_bytes: shared memory per CTA one fit needs, or -1 if it does not fit / is not supported.
+ * dnmf_mu_fit_resident_cluster_size: CTAs per fit for this shape (1, or the cluster size 2..16; 0 = unsupported).
  */
 int64_t dnmf_mu_fit_resident_smem_bytes(int64_t m, int64_t n, int64_t k, int kl, int dtype);
+int dnmf_mu_fit_resident_cluster_size(int64_t m, int64_t n, int64_t k, int kl, int dtype);
 int dnmf_mu_fit_resident(const void* const* A_ptrs, int64_t lda, void* const* W_ptrs, void* const* H_ptrs, int64_t batch,
                          int64_t m, int64_t n, int64_t k, int kl, int w_update, int64_t it_begin, int64_t it_end,
                          double eps, int dtype, void* stream);

@@ -72,12 +72,13 @@ SIGNATURES = {
     'dnmf_posneg_colsumsq': (i32, [vp, i64, i64, i64, vp, vp]),
     'dnmf_nnsvd_pick': (i32, [vp, i64, i64, i64, vp, vp, vp, i64, i32, vp]),
     'dnmf_mu_fit_resident_smem_bytes': (i64, [i64, i64, i64, i32, i32]),
+    'dnmf_mu_fit_resident_cluster_size': (i32, [i64, i64, i64, i32, i32]),
     'dnmf_mu_fit_resident': (i32, [vp, i64, vp, vp, i64, i64, i64, i64, i32, i32, i64, i64, dbl, i32, vp]),
 }
 
 _NO_STATUS = {'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
               'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile', 'dnmf_colsum_workspace_bytes',
-              'dnmf_matvec_workspace_bytes', 'dnmf_mu_fit_resident_smem_bytes'}
+              'dnmf_matvec_workspace_bytes', 'dnmf_mu_fit_resident_smem_bytes', 'dnmf_mu_fit_resident_cluster_size'}
 
 
 class DnmfError(RuntimeError):

@@ -460,6 +460,13 @@ class DeviceOps:
             return False
         return L.call('dnmf_mu_fit_resident_smem_bytes', int(m), int(n), int(k), 1 if norm.lower() == 'kl' else 0, _DT[dtype]) > 0
 
+    @staticmethod
+    def resident_fit_ctas(m, n, k, norm, dtype):
+        """CTAs per fit the on-chip path uses for this shape: 1, a cluster size 2..16, or 0 when it does not apply."""
+        if norm.lower() not in ('fro', 'kl') or dtype not in _DT:
+            return 0
+        return L.call('dnmf_mu_fit_resident_cluster_size', int(m), int(n), int(k), 1 if norm.lower() == 'kl' else 0, _DT[dtype])
+
     def mu_fit_resident(self, As, Ws, Hs, norm, w_update, it_begin, it_end, eps):
         """Iterations [it_begin, it_end) of the MU loop (+ every-10th clamp) for len(As) independent fits in one launch;
         W and H are updated in place."""

@@ -237,7 +237,8 @@ def test_errors(ops):
 # ---- whole-fit on-chip multiplicative updates (dnmf_mu_fit_resident) --------------------------------------------
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
 @pytest.mark.parametrize('norm', ['fro', 'kl'])
-@pytest.mark.parametrize('m,n,k', [(96, 21, 4), (40, 64, 7), (130, 33, 1), (17, 200, 16), (64, 48, 64)])
+@pytest.mark.parametrize('m,n,k', [(96, 21, 4), (40, 64, 7), (130, 33, 1), (17, 200, 16), (64, 48, 64), (1024, 256, 4),
+                                   (300, 100, 8), (2050, 64, 5), (515, 300, 32)])
 def test_resident_fit_equals_per_kernel_loop(dtype, norm, m, n, k):
     """The on-chip loop follows the per-kernel update + clamp sequence (same math, different summation order)."""
     import torch
@@ -292,7 +293,9 @@ def test_resident_fit_limits():
     import torch
     from pydnmfk_b200 import device as D
     ops = D.default_ops()
-    assert ops.resident_fit_fits(96, 21, 10, 'kl', torch.float32)
-    assert not ops.resident_fit_fits(1024, 256, 4, 'kl', torch.float32)       # 1 MiB shard + U: more than one SM holds
+    assert ops.resident_fit_fits(96, 21, 10, 'kl', torch.float32) and ops.resident_fit_ctas(96, 21, 10, 'kl', torch.float32) == 1
+    assert ops.resident_fit_ctas(1024, 256, 4, 'kl', torch.float32) == 16     # swim: a 16-CTA cluster, 64 rows per CTA
+    assert ops.resident_fit_ctas(130, 33, 1, 'fro', torch.float64) == 2
+    assert not ops.resident_fit_fits(8192, 4096, 4, 'kl', torch.float32)      # 128 MiB: the A-streaming path
     assert not ops.resident_fit_fits(96, 21, 65, 'fro', torch.float32)
     assert not ops.resident_fit_fits(96, 21, 4, 'l1', torch.float32)

@@ -1,7 +1,7 @@
 """Secondary configurations of BASELINE.json / SURVEY.md section 8d, measured through the public API on ONE GPU
 (bench.py stays on the headline configuration, cfg2).  One JSON line per configuration:
 
-  cfg1   1024 x 256  k=4   FRO-MU and KL-MU, itr iterations (swim-sized; launch-bound, CUDA-graph replay)
+  cfg1   1024 x 256  k=4   FRO-MU and KL-MU, itr iterations (swim-sized; the whole fit runs on one thread-block cluster)
   cfg4   131072 x 65536 k=16 FRO-HALS and FRO-BCD (32 GiB shard; 2 resp. 3 A passes per iteration)
   cfg5   96 x 21 (wtsi-sized) NMFk ensemble: 20 perturbations x KL-MU itr=1000 for k = 2..10, wall time
 
@@ -69,7 +69,7 @@ if 'cfg1' in only:
     for norm in ('fro', 'kl'):
         dt, err = per_iteration(A, 4, norm, 'mu', 200, 2200)
         out[norm] = {'us_per_iteration': dt * 1e6, 'iters_per_s': 1.0 / dt, 'recon_err': err}
-    print(json.dumps({'config': 'cfg1: 1024x256 fp32 k=4 MU, 1 GPU, PyNMF.fit (CUDA-graph replay)', 'by_norm': out}), flush=True)
+    print(json.dumps({'config': 'cfg1: 1024x256 fp32 k=4 MU, 1 GPU, PyNMF.fit (whole fit on a 16-CTA thread-block cluster)', 'by_norm': out}), flush=True)
 
 if 'cfg4' in only:
     m, n, k = args.cfg4_rows, 65536, 16
