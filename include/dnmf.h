@@ -15,7 +15,9 @@
  *     with an explicit leading dimension (elements, not bytes).
  *   - dtype: DNMF_F32 / DNMF_F64 (the reference's --precision float32/float64).
  *   - math_mode: DNMF_MATH_ACCURATE = fp32-accurate results (FFMA, or 3xTF32
- *     split on the tcgen05 path); DNMF_MATH_TF32 = single-pass TF32.
+ *     split on the tcgen05 path).  DNMF_MATH_TF32 (single-pass TF32) is
+ *     reserved: this build computes DNMF_MATH_ACCURATE results for both values
+ *     (single-pass TF32 cannot meet the parity tolerance of the update loop).
  *   - stream: a cudaStream_t passed as void* (0 = legacy default stream).
  *   - the library never allocates persistent device memory; scratch space is
  *     passed in (`ws`, `ws_bytes`; size from dnmf_workspace_bytes()).
