@@ -287,8 +287,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(bar(iSE + ss));          // S slot may be overwritten
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(u[j]);
-          lo[j] = __float_as_uint(tf32_round_up(v - tf32_hi(v, hi_mode)));
+          lo[j] = tf32_lo_bits(u[j]);
         }
         TC_T(t_div);
         mbar_wait(bar(iTE + ts), pt ^ 1u);

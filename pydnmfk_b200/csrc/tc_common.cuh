@@ -218,6 +218,14 @@ __device__ __forceinline__ float tf32_round_up(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// The splitters' hot loop, 3 instructions per element (LOP3, FADD, IADD): the low part a - trunc_tf32(a) (exact), biased by
+// half a tf32 ulp so that the tensor core's own truncation of the operand rounds it to nearest.  Only valid on hardware
+// whose kind::tf32 truncates (checked once by calibrate(); otherwise the tensor path is switched off).
+__device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t raw) {
+  const float v = __uint_as_float(raw);
+  return __float_as_uint(v - __uint_as_float(raw & 0xFFFFE000u)) + 0x1000u;
+}
+
 
 // cycle accounting (dnmf_set_tc_profile): per-role time split written to a debug buffer; off in production
 #define TC_T(var) do { if (prof) { const long long _n = clock64(); var += _n - tprev; tprev = _n; } } while (0)
