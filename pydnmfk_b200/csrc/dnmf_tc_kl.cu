@@ -277,9 +277,9 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j) {
             const float den = (__uint_as_float(s0[j]) + __uint_as_float(s1[j])) + eps;
             const float a = __uint_as_float(u[j]);
-            // alternate SFU (MUFU.RCP) and FMA-pipe (Newton) reciprocals: the 32 divisions per thread and tile are the
-            // splitter's largest cost
-            u[j] = __float_as_uint((j & 1) ? div_newton(a, den) : __fdividef(a, den));
+            // den >= eps > 0 and far from overflow: one MUFU.RCP (1 ulp) and one multiply, no range handling.  The
+            // rounding errors of the 65536 quotients of a row are independent and average out in the contraction.
+            u[j] = __float_as_uint(a * rcp_approx(den));
           }
         }
         tc_fence_before();
