@@ -90,9 +90,7 @@ if 'cfg4' in only:
 
 if 'cfg5' in only:
     import tempfile
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
-    from oracle import nmfk_cases as K      # the 96 x 21 example matrix fixture only (no oracle compute)
-    A = K.wtsi().astype(np.float32)
+    A = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden', 'wtsi_X.npy')).astype(np.float32)
     with tempfile.TemporaryDirectory() as tmp:
         def nmfk(end_k, itr):
             p = params(2, 'kl', 'mu', itr, 96, 21)
