@@ -328,8 +328,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // small-operand split: Bcat = [hi(B) ; B - hi(B)] with the reduced dimension contiguous (K-major)
 // ---------------------------------------------------------------------------------------------------------
 // AH: B = H [k x n] (already K-major)
+// (k real factor rows, kp = padded count the kernel is instantiated for: rows [k, kp) of both halves stay zero)
 __global__ void __launch_bounds__(256) tc_split_h_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Bcat,
-                                                         int64_t ldb, int k, int64_t n) {
+                                                         int64_t ldb, int k, int kp, int64_t n) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)k * n) return;
   const int j = (int)(idx / n);
@@ -337,11 +338,11 @@ __global__ void __launch_bounds__(256) tc_split_h_kernel(const float* __restrict
   const float h = H[(int64_t)j * ldh + c];
   const float hi = tf32_hi(h, 1);     // nearest: the low part is then signed and half as large
   Bcat[(int64_t)j * ldb + c] = hi;
-  Bcat[(int64_t)(k + j) * ldb + c] = h - hi;
+  Bcat[(int64_t)(kp + j) * ldb + c] = h - hi;
 }
 // WTA: B = W^T, W is [m x k]: transpose through shared memory (coalesced both ways)
 __global__ void __launch_bounds__(256) tc_split_wt_kernel(const float* __restrict__ W, int64_t ldw, float* __restrict__ Bcat,
-                                                          int64_t ldb, int k, int64_t m) {
+                                                          int64_t ldb, int k, int kp, int64_t m) {
   __shared__ float tile[64][65];
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(256) tc_split_wt_kernel(const float* __restric
       const float w = tile[r][j];
       const float hi = tf32_hi(w, 1);
       Bcat[(int64_t)j * ldb + r0 + r] = hi;
-      Bcat[(int64_t)(k + j) * ldb + r0 + r] = w - hi;
+      Bcat[(int64_t)(kp + j) * ldb + r0 + r] = w - hi;
     }
   }
 }
@@ -401,6 +402,8 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
 }
 
 }  // namespace
+
+int tc_padded_k(int k) { return k <= 16 ? 16 : (k <= 32 ? 32 : 64); }
 
 TcPlan tc_plan(int64_t x_len, int64_t r_len, int k) {
   TcPlan p;
@@ -462,18 +465,23 @@ int tc_run(int mode, const float* A, int64_t lda, const float* B, int64_t ldbsrc
            int64_t m, int64_t n, int k, int transposed_out, int hi_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
   const int64_t x_len = mode == 0 ? m : n;
   const int64_t r_len = mode == 0 ? n : m;
-  const TcPlan pl = tc_plan(x_len, r_len, k);
+  const int kp = tc_padded_k(k);      // the kernels exist for 16 / 32 / 64 factor columns: smaller k ride along zero-padded
+  const TcPlan pl = tc_plan(x_len, r_len, kp);
   const int64_t need = pl.bcat_bytes + pl.partial_bytes;
   if (ws == nullptr || ws_bytes < need)
     return fail(DNMF_E_WORKSPACE, "tcgen05 pass needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
   if (((uintptr_t)ws % 256) != 0) return fail(DNMF_E_ARG, "workspace must be 256-byte aligned");
   float* Bcat = reinterpret_cast<float*>(ws);
   float* P = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + pl.bcat_bytes);
+  if (kp != k) {
+    cudaError_t e = cudaMemsetAsync(Bcat, 0, (size_t)pl.bcat_bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "Bcat memset");
+  }
   if (mode == 0) {
-    tc_split_h_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(B, ldbsrc, Bcat, pl.ldb, k, n);
+    tc_split_h_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(B, ldbsrc, Bcat, pl.ldb, k, kp, n);
     DNMF_LAUNCH_CHECK("tc_split_h_kernel");
   } else {
-    tc_split_wt_kernel<<<(unsigned)ceil_div(m, 64), 256, 0, st>>>(B, ldbsrc, Bcat, pl.ldb, k, m);
+    tc_split_wt_kernel<<<(unsigned)ceil_div(m, 64), 256, 0, st>>>(B, ldbsrc, Bcat, pl.ldb, k, kp, m);
     DNMF_LAUNCH_CHECK("tc_split_wt_kernel");
   }
   alignas(64) CUtensorMap tmA, tmB;
@@ -481,19 +489,19 @@ int tc_run(int mode, const float* A, int64_t lda, const float* B, int64_t ldbsrc
   if (mode == 0) rc = make_map(&tmA, A, m, n, lda, TC_BK, TC_BM);
   else rc = make_map(&tmA, A, m, n, lda, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  rc = make_map(&tmB, Bcat, 2 * k, r_len, pl.ldb, TC_BK, 2 * k);
+  rc = make_map(&tmB, Bcat, 2 * kp, r_len, pl.ldb, TC_BK, 2 * kp);
   if (rc) return rc;
-  const int64_t split_stride = x_len * k;
-  rc = mode == 0 ? launch_pass_k<0>(k, tmA, tmB, P, split_stride, x_len, pl, hi_mode, st)
-                 : launch_pass_k<1>(k, tmA, tmB, P, split_stride, x_len, pl, hi_mode, st);
+  const int64_t split_stride = x_len * kp;
+  rc = mode == 0 ? launch_pass_k<0>(kp, tmA, tmB, P, split_stride, x_len, pl, hi_mode, st)
+                 : launch_pass_k<1>(kp, tmA, tmB, P, split_stride, x_len, pl, hi_mode, st);
   if (rc) return rc;
-  // fixed-order sum of the split partials P[s][x][kk]  ->  out
+  // fixed-order sum of the split partials P[s][x][kk]  ->  out  (only the k real columns)
   int64_t so_r, so_c;   // strides of (x, kk) in the output
   if (mode == 0) { so_r = ldo; so_c = 1; }                        // V[x][kk]
   else if (transposed_out) { so_r = ldo; so_c = 1; }              // Y^T[x][kk]
   else { so_r = 1; so_c = ldo; }                                  // Y[kk][x]
   reduce_partials_kernel<float><<<(unsigned)ceil_div(x_len * k, 256), 256, 0, st>>>(P, split_stride, pl.splits, x_len, k,
-                                                                                     out, so_r, so_c);
+                                                                                     out, so_r, so_c, kp);
   DNMF_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }
@@ -565,11 +573,11 @@ int tc_hi_mode() { return g_hi_mode; }
 unsigned long long* tc_prof_ptr() { return g_prof; }
 int tc_dbg_flags() { return getenv("DNMF_TC_DBG") ? atoi(getenv("DNMF_TC_DBG")) : 0; }
 void tc_launch_split_h(const float* H, int64_t ldh, float* Bcat, int64_t ldb, int k, int64_t n, cudaStream_t st) {
-  tc_split_h_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(H, ldh, Bcat, ldb, k, n);
+  tc_split_h_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(H, ldh, Bcat, ldb, k, k, n);
   tls().launches++;
 }
 void tc_launch_split_wt(const float* W, int64_t ldw, float* Bcat, int64_t ldb, int k, int64_t m, cudaStream_t st) {
-  tc_split_wt_kernel<<<(unsigned)ceil_div(m, 64), 256, 0, st>>>(W, ldw, Bcat, ldb, k, m);
+  tc_split_wt_kernel<<<(unsigned)ceil_div(m, 64), 256, 0, st>>>(W, ldw, Bcat, ldb, k, k, m);
   tls().launches++;
 }
 
@@ -579,7 +587,8 @@ bool tc_eligible(int op, const void* A, int64_t lda, int64_t m, int64_t n, int64
   if (op != DNMF_OP_AH && op != DNMF_OP_WTA && !kl) return false;
   if (kl && !tc_kl_supported(k)) return false;
   if (dtype != DNMF_F32) return false;
-  if (!(k == 16 || k == 32 || k == 64)) return false;
+  if (k < 1 || k > 64) return false;
+  if (kl && k != 32) return false;
   if (((uintptr_t)A % 16) != 0 || (lda % 4) != 0) return false;
   if (g_min_elems < 0) {
     const char* env = getenv("DNMF_TC_MIN_ELEMS");
@@ -596,9 +605,9 @@ void tc_set_profile(void* buf) { g_prof = reinterpret_cast<unsigned long long*>(
 void tc_set_min_elems(int64_t elems) { g_min_elems = elems < 0 ? 0 : elems; }
 
 int64_t tc_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype) {
-  if (dtype != DNMF_F32 || !(k == 16 || k == 32 || k == 64)) return 0;
-  if (op == DNMF_OP_AH) { const TcPlan p = tc_plan(m, n, (int)k); return p.bcat_bytes + p.partial_bytes; }
-  if (op == DNMF_OP_WTA) { const TcPlan p = tc_plan(n, m, (int)k); return p.bcat_bytes + p.partial_bytes; }
+  if (dtype != DNMF_F32 || k < 1 || k > 64) return 0;
+  if (op == DNMF_OP_AH) { const TcPlan p = tc_plan(m, n, tc_padded_k((int)k)); return p.bcat_bytes + p.partial_bytes; }
+  if (op == DNMF_OP_WTA) { const TcPlan p = tc_plan(n, m, tc_padded_k((int)k)); return p.bcat_bytes + p.partial_bytes; }
   if ((op == DNMF_OP_KL_UHT || op == DNMF_OP_KL_WTU) && tc_kl_supported(k)) return tc_kl_workspace_bytes(op, m, n, k);
   return 0;
 }

@@ -493,7 +493,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   else if (transposed_out) { so_r = ldo; so_c = 1; }
   else { so_r = 1; so_c = ldo; }
   reduce_partials_kernel<float><<<(unsigned)ceil_div(x_len * k, 256), 256, 0, st>>>(P, split_stride, pl.splits, x_len, k, out,
-                                                                                     so_r, so_c);
+                                                                                     so_r, so_c, k);
   DNMF_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }

@@ -273,16 +273,17 @@ col_pass_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ W, i
   }
 }
 
-// out[r*so_r + c*so_c] = sum_{s < splits, in order} P[s*split_stride + r*C + c]
+// out[r*so_r + c*so_c] = sum_{s < splits, in order} P[s*split_stride + r*ldp + c]   (ldp >= C: padded partial rows)
 template <typename T>
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const T* __restrict__ P, int64_t split_stride, int splits, int64_t R, int64_t C,
-                       T* __restrict__ out, int64_t so_r, int64_t so_c) {
+                       T* __restrict__ out, int64_t so_r, int64_t so_c, int64_t ldp) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * C) return;
-  T acc = P[idx];
-  for (int s = 1; s < splits; ++s) acc += P[(int64_t)s * split_stride + idx];
   const int64_t r = idx / C, c = idx % C;
+  const int64_t src = r * ldp + c;
+  T acc = P[src];
+  for (int s = 1; s < splits; ++s) acc += P[(int64_t)s * split_stride + src];
   out[r * so_r + c * so_c] = acc;
 }
 

@@ -34,7 +34,7 @@ inline int launch_reduce(const T* P, int64_t split_stride, int splits, int64_t R
                   int64_t so_c, cudaStream_t st) {
   const int64_t tot = R * C;
   if (tot == 0) return 0;
-  reduce_partials_kernel<T><<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(P, split_stride, splits, R, C, out, so_r, so_c);
+  reduce_partials_kernel<T><<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(P, split_stride, splits, R, C, out, so_r, so_c, C);
   DNMF_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }

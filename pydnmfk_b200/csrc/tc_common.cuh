@@ -246,6 +246,7 @@ struct TcPlan {
   int64_t ldb;            // leading dimension of Bcat (reduced length rounded up to 4)
   int64_t bcat_bytes, partial_bytes;
 };
+int tc_padded_k(int k);
 TcPlan tc_plan(int64_t x_len, int64_t r_len, int k);
 int tc_hi_mode();                       // 0: the tensor core truncates fp32 -> tf32, 1: rounds to nearest (calibrated)
 unsigned long long* tc_prof_ptr();      // debug buffer or nullptr

@@ -1,4 +1,4 @@
-"""The tcgen05 / TMA / TMEM path of the A-streaming contractions (fp32, k in {16, 32, 64}).
+"""The tcgen05 / TMA / TMEM path of the A-streaming contractions (fp32, k <= 64; kernels for 16 / 32 / 64, zero-padded).
 
 Checked three ways: bit-exact on small-integer data (every product and partial sum is exact in tf32/fp32, so
 any descriptor / swizzle / layout mistake shows up as a hard mismatch), against float64 numpy on random data
@@ -16,7 +16,9 @@ from tests import common as T
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(128, 32, 16), (128, 64, 32), (256, 96, 64), (1000, 1000, 32), (515, 2052, 32), (2048, 2048, 32),
-          (4100, 300, 64), (3000, 5000, 16), (1024, 8192, 32), (8192, 1024, 32), (129, 4100, 64)]
+          (4100, 300, 64), (3000, 5000, 16), (1024, 8192, 32), (8192, 1024, 32), (129, 4100, 64),
+          # factor widths between the instantiated 16 / 32 / 64 ride along zero-padded
+          (1000, 1000, 4), (2048, 2048, 10), (515, 2052, 20), (4100, 300, 48), (3000, 5000, 1), (640, 640, 33)]
 
 
 @pytest.fixture(scope='module')
