@@ -572,12 +572,12 @@ int tc_make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, 
 int tc_hi_mode() { return g_hi_mode; }
 unsigned long long* tc_prof_ptr() { return g_prof; }
 int tc_dbg_flags() { return getenv("DNMF_TC_DBG") ? atoi(getenv("DNMF_TC_DBG")) : 0; }
-void tc_launch_split_h(const float* H, int64_t ldh, float* Bcat, int64_t ldb, int k, int64_t n, cudaStream_t st) {
-  tc_split_h_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(H, ldh, Bcat, ldb, k, k, n);
+void tc_launch_split_h(const float* H, int64_t ldh, float* Bcat, int64_t ldb, int k, int kp, int64_t n, cudaStream_t st) {
+  tc_split_h_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(H, ldh, Bcat, ldb, k, kp, n);
   tls().launches++;
 }
-void tc_launch_split_wt(const float* W, int64_t ldw, float* Bcat, int64_t ldb, int k, int64_t m, cudaStream_t st) {
-  tc_split_wt_kernel<<<(unsigned)ceil_div(m, 64), 256, 0, st>>>(W, ldw, Bcat, ldb, k, k, m);
+void tc_launch_split_wt(const float* W, int64_t ldw, float* Bcat, int64_t ldb, int k, int kp, int64_t m, cudaStream_t st) {
+  tc_split_wt_kernel<<<(unsigned)ceil_div(m, 64), 256, 0, st>>>(W, ldw, Bcat, ldb, k, kp, m);
   tls().launches++;
 }
 
@@ -588,7 +588,6 @@ bool tc_eligible(int op, const void* A, int64_t lda, int64_t m, int64_t n, int64
   if (kl && !tc_kl_supported(k)) return false;
   if (dtype != DNMF_F32) return false;
   if (k < 1 || k > 64) return false;
-  if (kl && k != 32) return false;
   if (((uintptr_t)A % 16) != 0 || (lda % 4) != 0) return false;
   if (g_min_elems < 0) {
     const char* env = getenv("DNMF_TC_MIN_ELEMS");

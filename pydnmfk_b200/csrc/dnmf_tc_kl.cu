@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(KL_THREADS, 1)
 tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmF, const float* __restrict__ Fx, int64_t ldfx, int64_t fr_rows_pad,
              float* __restrict__ P, int64_t split_stride, int64_t x_len, int x_blocks, int kt_total, int kt_per_split,
-             int num_units, int hi_mode, float eps, unsigned long long* __restrict__ prof) {
+             int num_units, int k_real, float eps, unsigned long long* __restrict__ prof) {
   using Cfg = KlCfg;
   constexpr int SA = Cfg::SA, SB = Cfg::SB, SF = Cfg::SF, NT = Cfg::NT, NS = Cfg::NS, NBUF = Cfg::NBUF, N2 = Cfg::N2;
   extern __shared__ uint8_t smem_raw[];
@@ -227,7 +227,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float* frow = Fx + x * ldfx;
 #pragma unroll
         for (int j = 0; j < KK; ++j) {
-          const float w = (x < x_len) ? frow[j] : 0.f;
+          const float w = (x < x_len && j < k_real) ? frow[j] : 0.f;      // factor columns beyond k: zero padding
           const float h = tf32_hi(w, 1);
           hi[j] = __float_as_uint(h);
           lo[j] = __float_as_uint(tf32_round_up(w - h));
@@ -375,18 +375,19 @@ __global__ void __launch_bounds__(256) kl_split_fr_kernel(const float* __restric
     }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
-    const int r = idx / k, j = idx % k;
+  // rows of KK entries: the k real factor columns, then zero padding
+  for (int idx = threadIdx.x; idx < 64 * KK; idx += 256) {
+    const int r = idx / KK, j = idx % KK;
     if (r0 + r < r_pad) {
-      const float w = tile[r][j];
+      const float w = j < k ? tile[r][j] : 0.f;
       const float hi = tf32_hi(w, 1);
-      FrCat[(r0 + r) * k + j] = hi;
-      FrCat[(r_pad + r0 + r) * k + j] = tf32_round_up(w - hi);
+      FrCat[(r0 + r) * KK + j] = hi;
+      FrCat[(r_pad + r0 + r) * KK + j] = tf32_round_up(w - hi);
     }
   }
 }
 
-// Ht[c][j] = H[j][c]
+// Ht[c][j] = H[j][c] for j < k, 0 for k <= j < KK
 __global__ void __launch_bounds__(256) kl_transpose_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Ht,
                                                            int64_t n, int k) {
   __shared__ float tile[64][33];
@@ -396,9 +397,9 @@ __global__ void __launch_bounds__(256) kl_transpose_kernel(const float* __restri
     tile[c][j] = (c0 + c < n) ? H[(int64_t)j * ldh + c0 + c] : 0.f;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
-    const int c = idx / k, j = idx % k;
-    if (c0 + c < n) Ht[(c0 + c) * k + j] = tile[c][j];
+  for (int idx = threadIdx.x; idx < 64 * KK; idx += 256) {
+    const int c = idx / KK, j = idx % KK;
+    if (c0 + c < n) Ht[(c0 + c) * KK + j] = j < k ? tile[c][j] : 0.f;
   }
 }
 
@@ -407,31 +408,32 @@ struct KlPlan {
   int64_t r_pad, frcat_bytes, ht_bytes;
 };
 
-KlPlan kl_plan(int mode, int64_t m, int64_t n, int k) {
+KlPlan kl_plan(int mode, int64_t m, int64_t n) {       // every size is for the padded factor width KK
   KlPlan p;
   const int64_t x_len = mode == 0 ? m : n, r_len = mode == 0 ? n : m;
-  p.base = tc_plan(x_len, r_len, k);
+  p.base = tc_plan(x_len, r_len, KK);
   p.r_pad = round_up(r_len, 64);
-  p.frcat_bytes = round_up(2 * p.r_pad * k * 4, 1024);
-  p.ht_bytes = round_up(n * (int64_t)k * 4, 1024);       // plain H^T (Fx of WTU; by-product for UHT)
+  p.frcat_bytes = round_up(2 * p.r_pad * KK * 4, 1024);
+  p.ht_bytes = round_up(n * (int64_t)KK * 4, 1024);      // plain H^T (Fx of WTU)
   return p;
 }
 
 }  // namespace
 
-bool tc_kl_supported(int64_t k) { return k == KK; }
+bool tc_kl_supported(int64_t k) { return k >= 1 && k <= KK; }
 
 int64_t tc_kl_workspace_bytes(int op, int64_t m, int64_t n, int64_t k) {
-  const KlPlan p = kl_plan(op == DNMF_OP_KL_UHT ? 0 : 1, m, n, (int)k);
+  const KlPlan p = kl_plan(op == DNMF_OP_KL_UHT ? 0 : 1, m, n);
   return p.base.bcat_bytes + p.frcat_bytes + p.ht_bytes + p.base.partial_bytes;
 }
 
-// ws = [Bcat | FrCat | Ht | partials]
+// ws = [Bcat | FrCat | Ht | partials].  The kernel is written for KK = 32 factor columns; smaller k ride along zero-padded
+// (zero columns of W / rows of H add nothing to S = W H, and their output columns are dropped by the final reduction).
 int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* out,
               int64_t ldo, int64_t m, int64_t n, int k, float eps, int transposed_out, void* ws, int64_t ws_bytes,
               cudaStream_t st) {
-  if (k != KK) return fail(DNMF_E_UNSUPPORTED, "tcgen05 KL path: k must be %d", KK);
-  const KlPlan kp = kl_plan(mode, m, n, k);
+  if (k < 1 || k > KK) return fail(DNMF_E_UNSUPPORTED, "tcgen05 KL path: k must be in [1, %d]", KK);
+  const KlPlan kp = kl_plan(mode, m, n);
   const TcPlan& pl = kp.base;
   const int64_t x_len = mode == 0 ? m : n, r_len = mode == 0 ? n : m;
   const int64_t need = pl.bcat_bytes + kp.frcat_bytes + kp.ht_bytes + pl.partial_bytes;
@@ -444,35 +446,41 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   float* Ht = reinterpret_cast<float*>(wsb + pl.bcat_bytes + kp.frcat_bytes);
   float* P = reinterpret_cast<float*>(wsb + pl.bcat_bytes + kp.frcat_bytes + kp.ht_bytes);
   const unsigned fr_blocks = (unsigned)ceil_div(kp.r_pad, 64);
+  if (k != KK) {
+    cudaError_t e = cudaMemsetAsync(Bcat, 0, (size_t)pl.bcat_bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "Bcat memset");
+  }
   const float* Fx;
   int64_t ldfx;
   if (mode == 0) {
     // UHT: GEMM2 B = split(H); GEMM1 r-side factor = H^T rows (columns of A); x-side factor = W rows
-    tc_launch_split_h(H, ldh, Bcat, pl.ldb, k, n, st);
+    tc_launch_split_h(H, ldh, Bcat, pl.ldb, k, KK, n, st);
     kl_split_fr_kernel<true><<<fr_blocks, 256, 0, st>>>(H, ldh, FrCat, r_len, kp.r_pad, k);
     DNMF_LAUNCH_CHECK("kl_split_fr_kernel<T>");
     Fx = W;
     ldfx = ldw;
   } else {
     // WTU: GEMM2 B = split(W^T); GEMM1 r-side factor = W rows; x-side factor = H^T rows (columns of A)
-    tc_launch_split_wt(W, ldw, Bcat, pl.ldb, k, m, st);
+    tc_launch_split_wt(W, ldw, Bcat, pl.ldb, k, KK, m, st);
     kl_split_fr_kernel<false><<<fr_blocks, 256, 0, st>>>(W, ldw, FrCat, r_len, kp.r_pad, k);
     DNMF_LAUNCH_CHECK("kl_split_fr_kernel<N>");
-    kl_transpose_kernel<<<(unsigned)ceil_div(n, 64), 256, 0, st>>>(H, ldh, Ht, n, k);    // plain H^T [n x k]
+    kl_transpose_kernel<<<(unsigned)ceil_div(n, 64), 256, 0, st>>>(H, ldh, Ht, n, k);    // H^T [n x KK], zero padded
     DNMF_LAUNCH_CHECK("kl_transpose_kernel");
     Fx = Ht;
-    ldfx = k;
+    ldfx = KK;
   }
   alignas(64) CUtensorMap tmA, tmB, tmF;
   int rc;
   if (mode == 0) rc = tc_make_map(&tmA, A, m, n, lda, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
   else rc = tc_make_map(&tmA, A, m, n, lda, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  rc = tc_make_map(&tmB, Bcat, 2 * k, r_len, pl.ldb, TC_BK, 2 * k, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = tc_make_map(&tmB, Bcat, 2 * KK, r_len, pl.ldb, TC_BK, 2 * KK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, k, k, k, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  const int64_t split_stride = x_len * k;
+  const int64_t split_stride = x_len * KK;
+  // (for UHT the x-side factor rows are read straight from W with its own leading dimension: only k_real columns exist)
+  const int k_real = mode == 0 ? k : KK;
   auto launch = [&](auto kern) -> int {
     static bool attr_set[2] = {false, false};
     if (!attr_set[mode]) {
@@ -482,7 +490,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
     }
     kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmB, tmF, Fx, ldfx, kp.r_pad, P, split_stride, x_len,
                                                           pl.x_blocks, pl.kt_total, pl.kt_per_split, pl.num_units,
-                                                          tc_hi_mode(), eps, tc_prof_ptr());
+                                                          k_real, eps, tc_prof_ptr());
     DNMF_LAUNCH_CHECK("tc_kl_kernel");
     return 0;
   };
@@ -493,7 +501,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   else if (transposed_out) { so_r = ldo; so_c = 1; }
   else { so_r = 1; so_c = ldo; }
   reduce_partials_kernel<float><<<(unsigned)ceil_div(x_len * k, 256), 256, 0, st>>>(P, split_stride, pl.splits, x_len, k, out,
-                                                                                     so_r, so_c, k);
+                                                                                     so_r, so_c, KK);
   DNMF_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }

@@ -253,8 +253,8 @@ unsigned long long* tc_prof_ptr();      // debug buffer or nullptr
 int tc_dbg_flags();
 
 // small-operand split kernels (dnmf_tc.cu)
-void tc_launch_split_h(const float* H, int64_t ldh, float* Bcat, int64_t ldb, int k, int64_t n, cudaStream_t st);
-void tc_launch_split_wt(const float* W, int64_t ldw, float* Bcat, int64_t ldb, int k, int64_t m, cudaStream_t st);
+void tc_launch_split_h(const float* H, int64_t ldh, float* Bcat, int64_t ldb, int k, int kp, int64_t n, cudaStream_t st);
+void tc_launch_split_wt(const float* W, int64_t ldw, float* Bcat, int64_t ldb, int k, int kp, int64_t m, cudaStream_t st);
 
 // fused KL contractions (dnmf_tc_kl.cu)
 int64_t tc_kl_workspace_bytes(int op, int64_t m, int64_t n, int64_t k);

@@ -113,12 +113,14 @@ def test_deterministic(ops):
 
 
 KL_SHAPES = [(128, 32, 32), (256, 96, 32), (1000, 1000, 32), (515, 2052, 32), (2048, 2048, 32), (4100, 300, 32),
-             (1024, 8192, 32), (8192, 1024, 32)]
+             (1024, 8192, 32), (8192, 1024, 32),
+             # k < 32 rides along zero-padded
+             (1000, 1000, 4), (2048, 2048, 10), (515, 2052, 20), (4100, 300, 1), (1024, 8192, 31)]
 
 
 @pytest.mark.parametrize('m,n,k', KL_SHAPES)
 def test_kl_tensor_path(ops, m, n, k):
-    """Fused KL contractions on the tcgen05 path (k = 32): S = W H recomputed on the tensor cores, U = A / (S + eps)
+    """Fused KL contractions on the tcgen05 path (k <= 32; the kernel is written for 32 factor columns): S = W H recomputed on the tensor cores, U = A / (S + eps)
     in the splitter warps, second MMA; compared with float64 numpy and with the generic fused kernels."""
     from pydnmfk_b200 import _lib as L
     rs = np.random.RandomState(3)
