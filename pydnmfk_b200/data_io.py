@@ -13,53 +13,63 @@ import numpy as np
 from .utils import determine_block_params, comm_timing
 
 
+def _load_npy(path):
+    return np.load(path)
+
+
+def _load_text(path):
+    return np.loadtxt(path, delimiter=',', ndmin=2)
+
+
+def _load_mat(path):
+    from scipy.io import loadmat
+    return loadmat(path)['X']
+
+
+# ftype -> (loader of the file at fpath + fname + suffix, whether every rank then keeps only its own block)
+_FORMATS = {'npy': (_load_npy, True), 'csv': (_load_text, True), 'txt': (_load_text, True), 'mat': (_load_mat, True),
+            'folder': (_load_npy, False)}
+
+
 class data_read():
+    """``data_read(args).read()`` -> this rank's shard as a C-contiguous array of ``args.precision``."""
+
     @comm_timing()
     def __init__(self, args):
-        self.fpath = args.fpath
+        self.fpath, self.fname, self.ftype = args.fpath, args.fname, args.ftype
         self.pgrid = args.grid if ("grid" in vars(args) and args.grid) else [args.p_r, args.p_c]
-        self.ftype = args.ftype
-        self.fname = args.fname
         self.comm = args.comm1
         self.rank = self.comm.rank
-        self.precision = args.precision if getattr(args, 'precision', None) else 'float32'
+        self.precision = getattr(args, 'precision', None) or 'float32'
         self.data = 0
-        if self.ftype == 'folder':
-            self.file_path = self.fpath + self.fname + str(self.comm.rank) + '.npy'
-        else:
-            self.file_path = self.fpath + self.fname + '.' + self.ftype
+        suffix = str(self.rank) + '.npy' if self.ftype == 'folder' else '.' + self.ftype
+        self.file_path = self.fpath + self.fname + suffix
 
     @comm_timing()
     def read(self):
         return self.read_dat()
 
+    # the reference's per-format entry points, kept for callers that use them directly
     def read_file_npy(self):
-        self.data = np.load(self.file_path)
+        self.data = _load_npy(self.file_path)
 
     def read_file_csv(self):
-        self.data = np.loadtxt(self.file_path, delimiter=',', ndmin=2)
+        self.data = _load_text(self.file_path)
 
     def read_file_mat(self):
-        from scipy.io import loadmat
-        self.data = loadmat(self.file_path)['X']
+        self.data = _load_mat(self.file_path)
 
     def data_partition(self):
-        blk = determine_block_params(self.rank, self.pgrid, self.data.shape).determine_block_index_range_asymm()
-        self.data = self.data[blk[0][0]:blk[1][0] + 1, blk[0][1]:blk[1][1] + 1]
+        (r0, c0), (r1, c1) = determine_block_params(self.rank, self.pgrid, self.data.shape).determine_block_index_range_asymm()
+        self.data = self.data[r0:r1 + 1, c0:c1 + 1]
 
     @comm_timing()
     def read_dat(self):
-        if self.ftype == 'npy':
-            self.read_file_npy()
-            self.data_partition()
-        elif self.ftype in ('csv', 'txt'):
-            self.read_file_csv()
-            self.data_partition()
-        elif self.ftype == 'mat':
-            self.read_file_mat()
-            self.data_partition()
-        if self.ftype == 'folder':
-            self.read_file_npy()
+        if self.ftype in _FORMATS:
+            loader, whole_matrix = _FORMATS[self.ftype]
+            self.data = loader(self.file_path)
+            if whole_matrix:
+                self.data_partition()
         return np.ascontiguousarray(self.data.astype(self.precision))
 
 
@@ -81,24 +91,19 @@ class data_write():
 
     @comm_timing()
     def save_factors(self, factors, reg=False):
-        self.create_folder_dir(self.fpath)
-        wdir, hdir = ('W_reg_factors/', 'H_reg_factors/') if reg else ('W_factors/', 'H_factors/')
+        tag = '_reg_factors/' if reg else '_factors/'
+        dirs = {'W': self.fpath + 'W' + tag, 'H': self.fpath + 'H' + tag}
         if self.rank == 0:
-            self.create_folder_dir(self.fpath + wdir)
-            self.create_folder_dir(self.fpath + hdir)
+            for d in dirs.values():
+                self.create_folder_dir(d)
         self.comm.barrier()
-        W, H = np.asarray(factors[0]), np.asarray(factors[1])
-        if self.p_r == 1 and self.p_c != 1:
-            if self.rank == 0:
-                np.save(self.fpath + wdir + 'W', W)
-            np.save(self.fpath + hdir + 'H_' + str(self.rank), H)
-        elif self.p_c == 1 and self.p_r != 1:
-            if self.rank == 0:
-                np.save(self.fpath + hdir + 'H', H)
-            np.save(self.fpath + wdir + 'W_' + str(self.rank), W)
-        else:
-            np.save(self.fpath + wdir + 'W_' + str(self.rank), W)
-            np.save(self.fpath + hdir + 'H_' + str(self.rank), H)
+        # a factor that is replicated over a 1-D grid is written once (by rank 0, without a rank suffix)
+        replicated = {'W': self.p_r == 1 and self.p_c != 1, 'H': self.p_c == 1 and self.p_r != 1}
+        for name, arr in zip(('W', 'H'), factors):
+            if not replicated[name]:
+                np.save(dirs[name] + name + '_' + str(self.rank), np.asarray(arr))
+            elif self.rank == 0:
+                np.save(dirs[name] + name, np.asarray(arr))
 
     @comm_timing()
     def save_cluster_results(self, params):

@@ -174,6 +174,18 @@ def test_data_io_formats(tmp_path):
         data_write(p).save_factors([W[r0:r1 + 1], H[:, c0:c1 + 1]], reg=True)
     Wr, Hr = read_factors(d + 'res/', (2, 2)).load_factors()
     assert np.array_equal(Wr, W) and np.array_equal(Hr, H)
+    # 1-D grids: the replicated factor is written once without a rank suffix (data_io.py:184-192)
+    for grid, once, per_rank in (((2, 1), 'H_reg_factors/H.npy', 'W_reg_factors/W_%d.npy'),
+                                 ((1, 2), 'W_reg_factors/W.npy', 'H_reg_factors/H_%d.npy')):
+        out = d + 'res_%dx%d/' % grid
+        for rank in range(2):
+            p = parse()
+            p.p_r, p.p_c, p.comm1, p.results_paths, p.ftype = grid[0], grid[1], _Comm(rank), out, 'npy'
+            data_write(p).save_factors([W[:3] + rank, H[:, :4] + rank], reg=True)
+        import os as _os
+        found = sorted(_os.path.join(dp, f)[len(out):] for dp, _, fs in _os.walk(out) for f in fs)
+        assert found == sorted([once, per_rank % 0, per_rank % 1]), found
+        assert np.array_equal(np.load(out + once), (H[:, :4] if once.startswith('H') else W[:3]))      # rank 0's copy
     stats = {'clusterSilhouetteCoefficients': np.array([0.9, 0.8]), 'avgSilhouetteCoefficients': 0.85, 'L_err': rs.rand(14),
              'L_errDist': 0.1, 'avgErr': 0.2, 'recon_err': [0.2, 0.21], 'AIC': -3.0}
     p = parse()
