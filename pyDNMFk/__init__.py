@@ -3,7 +3,7 @@
 import importlib
 import sys
 
-_MODULES = ('config', 'utils', 'dist_comm', 'dist_nmf', 'data_io', 'pyDNMF', 'dist_clustering', 'dist_svd', 'pyDNMFk')
+_MODULES = ('config', 'utils', 'dist_comm', 'dist_nmf', 'data_io', 'pyDNMF', 'dist_clustering', 'dist_svd', 'pyDNMFk', 'runner')
 for _m in _MODULES:
     _mod = importlib.import_module('pydnmfk_b200.' + _m)
     sys.modules[__name__ + '.' + _m] = _mod

@@ -196,3 +196,51 @@ def test_data_io_formats(tmp_path):
     assert np.array_equal(back['L_err'], stats['L_err']) and np.array_equal(back['ErrTol'], np.array(stats['recon_err']))
     write_results(d + 'res/', {'L_err': np.arange(3.0)})
     assert np.array_equal(read_results(d + 'res/')['L_err'], np.arange(3.0))
+
+
+def test_runner_front_end(monkeypatch, tmp_path):
+    """pyDNMFk_Runner (runner.py:12-191): defaults, argument checks, and that the runner object is the params bag handed
+    to data_read / PyNMF / PyNMFk with the grid, k range and communicators set."""
+    from pyDNMFk.runner import pyDNMFk_Runner
+    import pydnmfk_b200.runner as R
+    r = pyDNMFk_Runner()
+    assert (r.init, r.itr, r.norm, r.method, r.prune, r.precision, r.perturbations, r.noise_var, r.sill_thr, r.sampling,
+            r.process) == ('rand', 5000, 'kl', 'mu', False, 'float32', 20, 0.015, 0.6, 'uniform', 'pyDNMF')
+    assert pyDNMFk_Runner('nnsvd', 10).itr == 10
+    with pytest.raises(ValueError):
+        pyDNMFk_Runner(process='nmf')
+    with pytest.raises(TypeError):
+        pyDNMFk_Runner(iterations=3)
+    with pytest.raises(ValueError):
+        r.run(grid=[1, 1, 1])
+    seen = {}
+
+    class FakeRead:
+        def __init__(self, params):
+            seen['read'] = (params.fpath, params.fname, params.ftype, params.p_r, params.p_c, params.precision)
+
+        def read(self):
+            return np.ones((4, 3), dtype=np.float32)
+
+    class FakeNMF:
+        def __init__(self, A, factors=None, params=None):
+            seen['nmf'] = (A.shape, params.k, params.itr, params.grid, params.comm1.size, params.row_comm.size)
+
+        def fit(self):
+            return 'W', 'H', 0.25
+
+    class FakeNMFk(FakeNMF):
+        def __init__(self, A, factors=None, params=None):
+            seen['nmfk'] = (params.start_k, params.end_k, params.step_k, params.perturbations, params.sill_thr)
+
+        def fit(self):
+            return 3
+
+    monkeypatch.setattr(R, 'data_read', FakeRead)
+    monkeypatch.setattr(R, 'PyNMF', FakeNMF)
+    monkeypatch.setattr(R, 'PyNMFk', FakeNMFk)
+    out = pyDNMFk_Runner(itr=7).run(grid=[1, 1], fpath='d/', fname='x', ftype='npy', results_path=str(tmp_path) + '/', k=5)
+    assert out == {'W': 'W', 'H': 'H', 'err': 0.25}
+    assert seen['read'] == ('d/', 'x', 'npy', 1, 1, 'float32') and seen['nmf'] == ((4, 3), 5, 7, [1, 1], 1, 1)
+    out = pyDNMFk_Runner(process='pyDNMFk', perturbations=4, timing_stats=False).run(grid=[1, 1], k_range=[2, 6], step_k=2)
+    assert out == {'nopt': 3} and seen['nmfk'] == (2, 6, 2, 4, 0.6)
