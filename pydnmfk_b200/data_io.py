@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .utils import determine_block_params, comm_timing
+from .utils import determine_block_params, comm_timing, transform_H_index
 
 
 def _load_npy(path):
@@ -177,8 +177,7 @@ class read_factors():
             W_data = np.vstack(W_data)
         if ct_H > 1:
             if ct_W > 1:
-                p_r, p_c = self.p_grid
-                H_data = np.hstack([H_data[i * p_c + j] for j in range(p_c) for i in range(p_r)])
+                H_data = np.hstack([H_data[r] for r in transform_H_index(self.p_grid).rankidx2blkidx()])
             else:
                 H_data = np.hstack(H_data)
         self.W, self.H = W_data, H_data

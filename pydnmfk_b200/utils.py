@@ -183,6 +183,25 @@ class data_operations():
         return W, H
 
 
+class transform_H_index():
+    """Order in which the per-rank H shards of a p_r x p_c grid tile the columns of H (utils.py:345-364).
+
+    The shard of rank ``i * p_c + j`` covers sub-block ``i`` of block column ``j``, so the column order is
+    "for j: for i".  The reference computes ``i * p_r + j``, which is the same only for square grids; the rank index
+    used here is the one that reassembles H correctly on every grid (tests/test_host_logic.py, tests -m gpu).
+    """
+
+    def __init__(self, grid):
+        self.p_r = grid[0]
+        self.p_c = grid[1]
+
+    def rankidx2blkidx(self):
+        return [i * self.p_c + j for j in range(self.p_c) for i in range(self.p_r)]
+
+    def transform_H_idx(self, rank):
+        return self.rankidx2blkidx()[rank]
+
+
 def norm(X, comm, norm=2, axis=None, p=-1):
     """Distributed vector 2-norm (utils.py:367-391): local sum of squares on the device, optional
     all-reduce, square root.  Returns a python float."""

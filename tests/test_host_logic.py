@@ -244,3 +244,23 @@ def test_runner_front_end(monkeypatch, tmp_path):
     assert seen['read'] == ('d/', 'x', 'npy', 1, 1, 'float32') and seen['nmf'] == ((4, 3), 5, 7, [1, 1], 1, 1)
     out = pyDNMFk_Runner(process='pyDNMFk', perturbations=4, timing_stats=False).run(grid=[1, 1], k_range=[2, 6], step_k=2)
     assert out == {'nopt': 3} and seen['nmfk'] == (2, 6, 2, 4, 0.6)
+
+
+def test_transform_H_index_orders_shards_by_block_column():
+    from pydnmfk_b200.utils import transform_H_index
+    assert transform_H_index((2, 2)).rankidx2blkidx() == [0, 2, 1, 3]            # same as the reference on square grids
+    assert transform_H_index((4, 2)).rankidx2blkidx() == [0, 2, 4, 6, 1, 3, 5, 7]
+    assert transform_H_index((2, 3)).rankidx2blkidx() == [0, 3, 1, 4, 2, 5]
+    # cross-check with the oracle's shard geometry: concatenating the H shards in this order restores the columns
+    for p_r, p_c in ((2, 3), (4, 2), (3, 3)):
+        n = 37
+        cols = {}
+        for r in range(p_r * p_c):
+            i, j = divmod(r, p_c)
+            (_, c0), (_, c1) = O.block_range(r, (p_r, p_c), (5, n))               # block column j of A
+            width = c1 - c0 + 1
+            s = i * (width // p_r) + min(i, width % p_r)
+            e = (i + 1) * (width // p_r) + min(i + 1, width % p_r)
+            cols[r] = list(range(c0 + s, c0 + e))                                # sub-block i of block column j
+        order = transform_H_index((p_r, p_c)).rankidx2blkidx()
+        assert sum((cols[r] for r in order), []) == list(range(n))
