@@ -73,6 +73,33 @@ class data_read():
         return np.ascontiguousarray(self.data.astype(self.precision))
 
 
+class split_files_save():
+    """Cut a global matrix into the p_r x p_c blocks of ``determine_block_params`` and write them as ``A_<rank>.npy``
+    under ``fpath``: the layout ``ftype='folder'`` reads back (data_io.py:108-136; the reference's writer stores the whole
+    matrix in every file, this one stores each rank's block)."""
+
+    @comm_timing()
+    def __init__(self, data, pgrid, fpath):
+        self.data = data
+        self.pgrid = pgrid
+        self.p_r, self.p_c = pgrid[0], pgrid[1]
+        self.fpath = fpath
+        os.makedirs(self.fpath, exist_ok=True)
+
+    @comm_timing()
+    def split_files(self):
+        self.split = []
+        for rank in range(self.p_r * self.p_c):
+            (r0, c0), (r1, c1) = determine_block_params(rank, self.pgrid, self.data.shape).determine_block_index_range_asymm()
+            self.split.append(self.data[r0:r1 + 1, c0:c1 + 1])
+        return self.split
+
+    @comm_timing()
+    def save_data_to_file(self):
+        for rank, block in enumerate(self.split_files()):
+            np.save(self.fpath + 'A_' + str(rank) + '.npy', block)
+
+
 class data_write():
     """Per-rank factor files ``W_factors/W_<rank>.npy`` / ``H_factors/H_<rank>.npy`` (1-D grids write
     the replicated factor once), or ``*_reg_factors`` for the NMFk regression fit."""

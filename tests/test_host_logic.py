@@ -153,6 +153,10 @@ def test_data_io_formats(tmp_path):
     for rank in range(4):
         s, e = O.block_range(rank, (2, 2), X.shape)
         np.save(d + 'A_%d.npy' % rank, X[s[0]:e[0] + 1, s[1]:e[1] + 1])
+    from pydnmfk_b200.data_io import split_files_save
+    split_files_save(X, (2, 2), d + 'split/').save_data_to_file()
+    for rank in range(4):
+        assert np.array_equal(np.load(d + 'split/A_%d.npy' % rank), np.load(d + 'A_%d.npy' % rank))
     for ftype, fname in (('npy', 'X'), ('csv', 'X'), ('mat', 'X'), ('folder', 'A_')):
         for rank in range(4):
             p = parse()
