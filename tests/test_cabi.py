@@ -65,3 +65,29 @@ def test_no_cpu_fallback():
     for fn in os.listdir(pkg):
         if fn.endswith('.py'):
             assert 'oracle' not in open(os.path.join(pkg, fn)).read().replace('no oracle', ''), fn
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/dnmf.h compiles as C99 and a C program linked against libdnmf.so can call it (no GPU needed for the
+    version / error / workspace queries)."""
+    import shutil
+    import subprocess
+    from pydnmfk_b200 import _lib as L
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'cabi.c'
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "dnmf.h"\n'
+        'int main(void) {\n'
+        '  const char* v = dnmf_version();\n'
+        '  int64_t ws = dnmf_workspace_bytes(DNMF_OP_WTA, 4096, 4096, 32, DNMF_F32);\n'
+        '  int rc = dnmf_ah(0, 8, 0, 8, 0, 8, 8, 8, 4, DNMF_F32, DNMF_MATH_ACCURATE, 0, 0, 0);\n'
+        '  printf("%s|%lld|%d|%s\\n", v, (long long)ws, rc, dnmf_last_error());\n'
+        '  return strstr(v, "sm_100a") && ws > 0 && rc == DNMF_E_ARG ? 0 : 1;\n}\n')
+    exe = tmp_path / 'cabi'
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                    '-L', libdir, '-l:libdnmf.so', '-Wl,-rpath,' + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert 'sm_100a' in out and 'bad argument' in out
