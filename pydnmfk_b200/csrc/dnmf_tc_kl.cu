@@ -12,6 +12,9 @@
 // Both GEMMs use the 3-term tf32 split (see dnmf_tc.cu) so the result is fp32-accurate; U and U_lo go to the TMEM
 // operand ring like A and A_lo do on the FRO path.  The MMA warp issues GEMM1 two tiles ahead of GEMM2.
 //
+// MODE 2 (residual, opt-in via DNMF_TC_RESIDUAL=1, see tc_residual_run): the same GEMM1 and tile traffic, but the
+// splitters accumulate sum (A - S)^2 and sum A^2 instead of forming U; GEMM2, its B producer and the drain warps idle.
+//
 // Warp roles (512 threads, one persistent CTA per SM): w0 A-TMA | w1 MMA issuer | w2-5, w11-14 splitter groups |
 // w6-9 drain | w10 Bcat-TMA (lane 0) + Fr-TMA (lane 1) | w15 GEMM1 issuer.
 #include "generic_passes.cuh"
@@ -105,7 +108,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(bar(iAE + s), ph ^ 1u);
           mbar_expect_tx(bar(iAF + s), Cfg::A_BYTES);
-          if (MODE == 0) tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, bar(iAF + s), kt * TC_BK, xb * TC_BM);
+          if (MODE != 1) tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, bar(iAF + s), kt * TC_BK, xb * TC_BM);
           else tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, bar(iAF + s), xb * TC_BM, kt * TC_BK);
           if (++s == SA) { s = 0; ph ^= 1u; }
         }
@@ -113,7 +116,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 10) {
     // ===================== Bcat producer (lane 0, GEMM2 B operand) and FrCat producer (lane 1, GEMM1 B operand) =====
-    if (lane == 0) {
+    if (lane == 0 && MODE != 2) {
       int s = 0;
       uint32_t ph = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -179,7 +182,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int sb = 0, ts = 0, buf = 0;
     uint32_t pb = 0, pt = 0, accphase = 0;
     long long tprev = clock64(), t_acce = 0, t_tfull = 0, t_bfull = 0, t_g2 = 0, t0 = tprev;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+    for (int unit = blockIdx.x; MODE != 2 && unit < num_units; unit += gridDim.x) {
       const int sp = unit / x_blocks;
       const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
       const int ntiles = kt1 - kt0;
@@ -214,6 +217,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int group = (warp >= 11) ? 1 : 0;
     int tile = 0;
     uint32_t pxe = 0;
+    double res_sum = 0.0, a_sum = 0.0;      // MODE 2 only
     long long tprev = clock64(), t_afull = 0, t_load = 0, t_sfull = 0, t_div = 0, t_tfree = 0, t_store = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int xb = unit % x_blocks, sp = unit / x_blocks;
@@ -250,7 +254,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         TC_T(t_afull);
         const uint8_t* tl = base_ptr + sa * Cfg::A_BYTES;
         uint32_t u[32], lo[32];
-        if (MODE == 0) {
+        if (MODE != 1) {
           const uint8_t* row = tl + r * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -273,6 +277,26 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld_x32(saddr, s0);           // Fx_hi * Fr_hi
           tmem_ld_x32(saddr + 32, s1);      // Fx_hi * Fr_lo + Fx_lo * Fr_hi
           tmem_ld_wait();
+          if (MODE == 2) {
+            // residual: this row's 32 elements of (A - W H)^2 and A^2, fp32 within the tile, float64 across tiles
+            float t_res = 0.f, t_a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = __uint_as_float(u[j]);
+              const float d = a - (__uint_as_float(s0[j]) + __uint_as_float(s1[j]));
+              t_res = fmaf(d, d, t_res);
+              t_a = fmaf(a, a, t_a);
+            }
+            res_sum += (double)t_res;
+            a_sum += (double)t_a;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(bar(iSE + ss));       // S slot may be overwritten
+              mbar_arrive(bar(iAE + sa));       // every register loaded from the A tile has been consumed above
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float den = (__uint_as_float(s0[j]) + __uint_as_float(s1[j])) + eps;
@@ -304,6 +328,12 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(bar(iTF + ts));
       }
     }
+    if (MODE == 2) {
+      // one (residual, norm) pair per splitter thread; summed in a fixed order by the caller
+      double* pairs = reinterpret_cast<double*>(P) + ((int64_t)blockIdx.x * 256 + (group * 4 + q) * 32 + lane) * 2;
+      pairs[0] = res_sum;
+      pairs[1] = a_sum;
+    }
     if (prof && warp == 2 && lane == 0) {
       prof[blockIdx.x * 16 + 6] = t_afull; prof[blockIdx.x * 16 + 7] = t_load; prof[blockIdx.x * 16 + 8] = t_sfull;
       prof[blockIdx.x * 16 + 9] = t_div; prof[blockIdx.x * 16 + 10] = t_tfree; prof[blockIdx.x * 16 + 11] = t_store;
@@ -313,7 +343,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int q = warp & 3;
     int buf = 0;
     uint32_t accphase = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+    for (int unit = blockIdx.x; MODE != 2 && unit < num_units; unit += gridDim.x) {
       const int xb = unit % x_blocks, sp = unit / x_blocks;
       const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
       const int nchunks = (kt1 - kt0 + KL_CHUNK - 1) / KL_CHUNK;
@@ -503,6 +533,57 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   reduce_partials_kernel<float><<<(unsigned)ceil_div(x_len * k, 256), 256, 0, st>>>(P, split_stride, pl.splits, x_len, k, out,
                                                                                      so_r, so_c, KK);
   DNMF_LAUNCH_CHECK("reduce_partials_kernel");
+  return 0;
+}
+
+// ---- ||A - W H||^2 and ||A||^2 through the same pipeline (MODE 2) ---------------------------------------------------
+// Opt-in (DNMF_TC_RESIDUAL=1): written at the end of round 1 and NOT yet run on hardware; the default stays the
+// CUDA-core residual kernel.  ws = [FrCat | pairs (grid x 256 x 2 float64)]; out_pairs receives the per-thread pairs,
+// *n_pairs their count (the caller sums them in a fixed order).
+bool tc_residual_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DNMF_TC_RESIDUAL"); on = (e && atoi(e) != 0) ? 1 : 0; }
+  return on == 1;
+}
+
+int64_t tc_residual_workspace_bytes(int64_t m, int64_t n) {
+  const KlPlan p = kl_plan(0, m, n);
+  return p.frcat_bytes + round_up((int64_t)p.base.grid * 256 * 2 * (int64_t)sizeof(double), 1024);
+}
+
+int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, int64_t m,
+                    int64_t n, int k, void* ws, int64_t ws_bytes, double** out_pairs, int64_t* n_pairs, cudaStream_t st) {
+  if (k < 1 || k > KK) return fail(DNMF_E_UNSUPPORTED, "tcgen05 residual: k must be in [1, %d]", KK);
+  const KlPlan kp = kl_plan(0, m, n);
+  const TcPlan& pl = kp.base;
+  const int64_t need = tc_residual_workspace_bytes(m, n);
+  if (ws == nullptr || ws_bytes < need)
+    return fail(DNMF_E_WORKSPACE, "tcgen05 residual needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  if (((uintptr_t)ws % 256) != 0) return fail(DNMF_E_ARG, "workspace must be 256-byte aligned");
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  float* FrCat = reinterpret_cast<float*>(wsb);
+  double* pairs = reinterpret_cast<double*>(wsb + kp.frcat_bytes);
+  kl_split_fr_kernel<true><<<(unsigned)ceil_div(kp.r_pad, 64), 256, 0, st>>>(H, ldh, FrCat, n, kp.r_pad, k);
+  DNMF_LAUNCH_CHECK("kl_split_fr_kernel<T>");
+  alignas(64) CUtensorMap tmA, tmF;
+  int rc = tc_make_map(&tmA, A, m, n, lda, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  auto kern = tc_kl_kernel<2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, KlCfg::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "tc_kl_kernel<2> smem attribute");
+    attr_set = true;
+  }
+  // (the GEMM2 operand map is unused in this mode: tmF stands in for it)
+  kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmF, tmF, W, ldw, kp.r_pad, reinterpret_cast<float*>(pairs), 0, m,
+                                                        pl.x_blocks, pl.kt_total, pl.kt_per_split, pl.num_units, k, 0.f,
+                                                        tc_prof_ptr());
+  DNMF_LAUNCH_CHECK("tc_kl_kernel<2>");
+  *out_pairs = pairs;
+  *n_pairs = (int64_t)pl.grid * 256;
   return 0;
 }
 
