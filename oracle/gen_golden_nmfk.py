@@ -4,7 +4,8 @@ produced by the UNMODIFIED reference on forked ranks.  TEST INFRASTRUCTURE; auth
     python oracle/gen_golden_nmfk.py [cluster] [nnsvd] [nnsvdfit] [pvalue] [e2e]
 
 Writes tests/golden/nmfk_cases.npz, copies the reference's own small fixtures for this path (tests/sill.npy,
-tests/nnsvd_factors_*.npy -> tests/golden/ref_*.npy/.npz) and the 96x21 example matrix (data/wtsi.mat -> wtsi_X.npy).
+tests/nnsvd_factors_*.npy -> tests/golden/ref_*.npy/.npz) and the example matrices (data/wtsi.mat -> wtsi_X.npy, 96 x 21;
+data/swim.mat -> swim_X.npy, 1024 x 256).
 """
 import os
 import shutil
@@ -154,6 +155,7 @@ def main(argv):
     if 'fixtures' in what:
         from scipy.io import loadmat
         np.save(os.path.join(K.GOLDEN, 'wtsi_X.npy'), loadmat(os.path.join(REFERENCE, 'data', 'wtsi.mat'))['X'])
+        np.save(os.path.join(K.GOLDEN, 'swim_X.npy'), loadmat(os.path.join(REFERENCE, 'data', 'swim.mat'))['X'])
         shutil.copy(os.path.join(REFERENCE, 'tests', 'sill.npy'), os.path.join(K.GOLDEN, 'ref_sill.npy'))
         for t in ('24x16', '16x24'):
             f = np.load(os.path.join(REFERENCE, 'tests', 'nnsvd_factors_%s.npy' % t), allow_pickle=True).item()
