@@ -77,7 +77,8 @@ class custom_clustering():
         return ans
 
     def greedy_lsa(self, A):
-        """Pairs (centroid, feature) in pick order for one k x k similarity matrix (device kernel, k <= 64)."""
+        """The greedy assignment of one k x k similarity matrix as (centroid, feature) pairs, one per centroid (the
+        reference lists them in pick order; ``change_order`` gives the same result either way).  Device kernel, k <= 64."""
         t = D.to_device(np.ascontiguousarray(A) if not isinstance(A, torch.Tensor) else A).contiguous()
         k = t.shape[0]
         order = self.ops.greedy_lsa(t.view(k, k), k, 1).cpu().numpy()[0]

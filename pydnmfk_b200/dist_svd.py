@@ -104,7 +104,7 @@ class DistSVD():
     # ---- dist_svd.py:139-145 -------------------------------------------------------------------------------
     @comm_timing()
     def calc_norm(self, vec):
-        sq = self.grid_comm.allreduce_(self.ops.sqnorm(vec.view(1, -1)))
+        sq = self.grid_comm.allreduce_(self.ops.sqnorm(D.to_device(vec).contiguous().view(1, -1)))
         return float(np.sqrt(sq.item()))
 
     # ---- dist_svd.py:147-181 -------------------------------------------------------------------------------
