@@ -61,6 +61,10 @@ const char* dnmf_last_error(void);
 /* which code path the last dnmf_ah/dnmf_wta/dnmf_kl_* call on this thread took:
  * 0 = generic CUDA-core kernel, 1 = tcgen05 (TMA + UMMA + TMEM) kernel */
 int dnmf_last_path(void);
+/* A-streaming passes (dnmf_ah / dnmf_wta / dnmf_kl_*) issued on this thread since the last reset:
+ * which = 1: through the tcgen05 kernels, which = 0: through the generic CUDA-core kernels (parity tests assert
+ * that the large cases never touch the generic ones) */
+int64_t dnmf_pass_count(int which, int reset);
 /* number of kernels launched by this library on this thread since the last reset */
 int64_t dnmf_launch_count(int reset);
 int dnmf_device_info(int* sm_count, int* cc_major, int* cc_minor);

@@ -20,7 +20,7 @@ def _case(name, m, n, k, grid, norm, method, itr, dtype='float32', data='uniform
           seed=100, reseed=None, prune=False, W_update=True, given_factors=False, k0=None):
     return dict(name=name, m=m, n=n, k=k, grid=tuple(grid), norm=norm, method=method, itr=itr,
                 dtype=dtype, data=data, seed=seed, reseed=reseed, prune=prune,
-                W_update=W_update, given_factors=given_factors, k0=k0 or k)
+                W_update=W_update, given_factors=given_factors, k0=k0 or k, expect_tc=False)
 
 
 def draw_global(case, rs):
@@ -95,6 +95,23 @@ def _grid_cases():
     cs.append(_case('u256x384k16_1x1_fro_bcd_i10', 256, 384, 16, (1, 1), 'fro', 'bcd', 10, reseed=7))
     cs.append(_case('u256x384k64_1x1_fro_mu_i10', 256, 384, 64, (1, 1), 'fro', 'mu', 10, reseed=7))
     cs.append(_case('u256x384k64_4x2_fro_mu_i10', 256, 384, 64, (4, 2), 'fro', 'mu', 10, reseed=7))
+    # the tcgen05 path end to end: shards of >= 2^20 elements per rank (csrc/dnmf_tc.cu tc_eligible), so that every
+    # A-streaming pass of these fits runs tc_pass_kernel / tc_kl_kernel (asserted in tests/workers.py:fit_worker)
+    big = [
+        ('u2048', 2048, 2048, (1, 1), 'fro', 32, 100), ('u2048', 2048, 2048, (1, 1), 'fro', 10, 10),
+        ('u2048', 2048, 2048, (1, 1), 'fro', 64, 10), ('u2048', 2048, 2048, (1, 1), 'kl', 32, 100),
+        ('u2048', 2048, 2048, (1, 1), 'kl', 10, 10),
+        ('u2048', 2048, 2048, (2, 1), 'fro', 32, 10), ('u2048', 2048, 2048, (2, 1), 'kl', 32, 10),
+        ('u2048', 2048, 2048, (1, 2), 'fro', 32, 10), ('u2048', 2048, 2048, (1, 2), 'kl', 32, 10),
+        ('u2048', 2048, 2048, (2, 2), 'fro', 32, 10), ('u2048', 2048, 2048, (2, 2), 'kl', 32, 10),
+        ('u2048', 2048, 2048, (2, 2), 'fro', 64, 10),
+        ('u4096x1024', 4096, 1024, (1, 1), 'fro', 32, 10), ('u4096x1024', 4096, 1024, (2, 1), 'kl', 32, 100),
+        ('u4096x1024', 4096, 1024, (2, 2), 'fro', 64, 100), ('u4096x1024', 4096, 1024, (1, 1), 'kl', 10, 100),
+    ]
+    for tag, m, n, g, norm, k, itr in big:
+        c = _case('%sk%d_%dx%d_%s_mu_i%d' % (tag, k, g[0], g[1], norm, itr), m, n, k, g, norm, 'mu', itr, reseed=7)
+        c['expect_tc'] = True
+        cs.append(c)
     # prune path: exact-zero rows/cols, fp32 in -> float64 out (utils.py:195,198)
     for g in ((1, 1), (2, 1), (1, 2), (2, 2)):
         for norm in ('fro', 'kl'):

@@ -23,6 +23,7 @@ SIGNATURES = {
     'dnmf_last_error': (C.c_char_p, []),
     'dnmf_last_path': (i32, []),
     'dnmf_launch_count': (i64, [i32]),
+    'dnmf_pass_count': (i64, [i32, i32]),
     'dnmf_device_info': (i32, [C.POINTER(i32)] * 3),
     'dnmf_set_force_generic': (i32, [i32]),
     'dnmf_set_tc_min_elems': (i32, [i64]),
@@ -76,7 +77,7 @@ SIGNATURES = {
     'dnmf_mu_fit_resident': (i32, [vp, i64, vp, vp, i64, i64, i64, i64, i32, i32, i64, i64, dbl, i32, vp]),
 }
 
-_NO_STATUS = {'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
+_NO_STATUS = {'dnmf_pass_count', 'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
               'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile', 'dnmf_colsum_workspace_bytes',
               'dnmf_matvec_workspace_bytes', 'dnmf_mu_fit_resident_smem_bytes', 'dnmf_mu_fit_resident_cluster_size'}
 
@@ -132,6 +133,11 @@ def last_path():
 
 def launch_count(reset=False):
     return _lib.dnmf_launch_count(1 if reset else 0)
+
+
+def pass_count(tensor_path, reset=False):
+    """A-streaming passes issued since the last reset through the tcgen05 (True) or generic (False) kernels."""
+    return _lib.dnmf_pass_count(1 if tensor_path else 0, 1 if reset else 0)
 
 
 def set_force_generic(on):

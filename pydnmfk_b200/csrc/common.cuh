@@ -15,6 +15,8 @@ struct TlsState {
   int last_path;
   int64_t launches;
   int force_generic;
+  int64_t tc_passes;        // A-streaming passes routed to the tcgen05 kernels on this thread
+  int64_t generic_passes;   // ... and to the generic CUDA-core kernels
 };
 TlsState& tls();
 

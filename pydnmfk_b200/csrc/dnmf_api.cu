@@ -91,9 +91,11 @@ int dnmf_ah(const void* A, int64_t lda, const void* H, int64_t ldh, void* V, int
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_eligible(DNMF_OP_AH, A, lda, m, n, k, dtype)) {
     tls().last_path = 1;
+    tls().tc_passes++;
     return tc_ah((const float*)A, lda, (const float*)H, ldh, (float*)V, ldv, m, n, (int)k, math_mode, ws, ws_bytes, st);
   }
   tls().last_path = 0;
+  tls().generic_passes++;
   DISPATCH_T(dtype, return row_pass_dispatch<T>(false, (const T*)A, lda, (const T*)H, ldh, (const T*)nullptr, 0, (T*)V, ldv, m, n, (int)k, T(0), ws, ws_bytes, st));
   return 0;
 }
@@ -107,9 +109,11 @@ int dnmf_wta(const void* A, int64_t lda, const void* W, int64_t ldw, void* Y, in
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_eligible(DNMF_OP_WTA, A, lda, m, n, k, dtype)) {
     tls().last_path = 1;
+    tls().tc_passes++;
     return tc_wta((const float*)A, lda, (const float*)W, ldw, (float*)Y, ldy, m, n, (int)k, transposed_out, math_mode, ws, ws_bytes, st);
   }
   tls().last_path = 0;
+  tls().generic_passes++;
   DISPATCH_T(dtype, return col_pass_dispatch<T>(false, (const T*)A, lda, (const T*)W, ldw, (const T*)nullptr, 0, (T*)Y, ldy, m, n, (int)k, T(0), transposed_out, ws, ws_bytes, st));
   return 0;
 }
@@ -124,9 +128,11 @@ int dnmf_kl_uht(const void* A, int64_t lda, const void* W, int64_t ldw, const vo
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_eligible(DNMF_OP_KL_UHT, A, lda, m, n, k, dtype)) {
     tls().last_path = 1;
+    tls().tc_passes++;
     return tc_kl_uht((const float*)A, lda, (const float*)W, ldw, (const float*)H, ldh, (float*)V, ldv, m, n, (int)k, (float)eps, math_mode, ws, ws_bytes, st);
   }
   tls().last_path = 0;
+  tls().generic_passes++;
   DISPATCH_T(dtype, return row_pass_dispatch<T>(true, (const T*)A, lda, (const T*)H, ldh, (const T*)W, ldw, (T*)V, ldv, m, n, (int)k, (T)eps, ws, ws_bytes, st));
   return 0;
 }
@@ -141,9 +147,11 @@ int dnmf_kl_wtu(const void* A, int64_t lda, const void* W, int64_t ldw, const vo
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_eligible(DNMF_OP_KL_WTU, A, lda, m, n, k, dtype)) {
     tls().last_path = 1;
+    tls().tc_passes++;
     return tc_kl_wtu((const float*)A, lda, (const float*)W, ldw, (const float*)H, ldh, (float*)Y, ldy, m, n, (int)k, (float)eps, transposed_out, math_mode, ws, ws_bytes, st);
   }
   tls().last_path = 0;
+  tls().generic_passes++;
   DISPATCH_T(dtype, return col_pass_dispatch<T>(true, (const T*)A, lda, (const T*)W, ldw, (const T*)H, ldh, (T*)Y, ldy, m, n, (int)k, (T)eps, transposed_out, ws, ws_bytes, st));
   return 0;
 }

@@ -7,7 +7,7 @@
 namespace dnmf {
 
 TlsState& tls() {
-  static thread_local TlsState s = {{0}, 0, 0, 0};
+  static thread_local TlsState s = {{0}, 0, 0, 0, 0, 0};
   return s;
 }
 
@@ -68,6 +68,13 @@ int dnmf_last_path(void) { return tls().last_path; }
 int64_t dnmf_launch_count(int reset) {
   int64_t v = tls().launches;
   if (reset) tls().launches = 0;
+  return v;
+}
+
+int64_t dnmf_pass_count(int which, int reset) {
+  int64_t& c = which ? tls().tc_passes : tls().generic_passes;
+  const int64_t v = c;
+  if (reset) c = 0;
   return v;
 }
 

@@ -22,7 +22,8 @@ pytestmark = pytest.mark.gpu
 def _tol(case):
     tf, te = T.TOL_FACTOR[case['dtype']], T.TOL_ERR[case['dtype']]
     if case['method'] == 'bcd' and case['dtype'] == 'float32':
-        tf, te = 2e-3, 1e-3
+        # fp32 device path vs a reference that numpy >= 2 silently runs in float64; measured 7e-7
+        tf, te = 1e-4, 1e-4
     if case['data'] == 'lowrank':
         # exact rank-k data converges to err ~ 1e-9: the factors are then determined only up to the
         # conditioning of the problem; the reference's own test only asserts err < 1e-3
@@ -49,7 +50,8 @@ def _compare(case, res):
     for r, o in enumerate(res):
         g = gold[r]
         _log(dict(case=case['name'], rank=r, relW=T.rel_fro(o['W'], g['W']), relH=T.rel_fro(o['H'], g['H']),
-                  err=o['err'], err_ref=float(g['err']), tol_factor=tf, tol_err=te))
+                  err=o['err'], err_ref=float(g['err']), tol_factor=tf, tol_err=te,
+                  tc_passes=o.get('tc_passes'), generic_passes=o.get('generic_passes')))
         assert o['geom'] == [int(v) for v in g['geom'][:8]], 'shard geometry differs on rank %d' % r
         assert o['W'].shape == g['W'].shape and o['H'].shape == g['H'].shape
         if case['method'] != 'bcd':
@@ -80,7 +82,7 @@ def _run(case, force_generic=False, resident=True):
 SINGLE = [c for c in C.CASES if c['grid'] == (1, 1)]
 MULTI = [c for c in C.CASES if c['grid'] != (1, 1)]
 # a representative multi-rank subset keeps the GPU suite to a few minutes (process spawn dominates)
-MULTI_PICK = [c for c in MULTI if c['itr'] in (10, 300) or c['prune'] or c['given_factors']]
+MULTI_PICK = [c for c in MULTI if c['itr'] in (10, 300) or c['prune'] or c['given_factors'] or c['expect_tc']]
 MULTI_PICK = [c for c in MULTI_PICK if not (c['name'].startswith('u64x48k4') and c['dtype'] == 'float64' and c['grid'] in ((1, 2), (4, 2)))]
 
 
@@ -127,12 +129,18 @@ def test_multi_rank_matches_reference(case):
     _compare(case, _multi_results(case))
 
 
-@pytest.mark.parametrize('name', ['u512k32_1x1_fro_mu_i100', 'u512k32_1x1_kl_mu_i100', 'u256x384k64_1x1_fro_mu_i10'])
+@pytest.mark.parametrize('name', ['u2048k32_1x1_fro_mu_i100', 'u2048k32_1x1_kl_mu_i100', 'u2048k64_1x1_fro_mu_i10',
+                                  'u2048k10_1x1_kl_mu_i10'])
 def test_generic_and_tensor_core_paths_agree_with_reference(name):
-    """Both device code paths (tcgen05 and generic CUDA-core) are held to the same reference tolerance."""
+    """Both device code paths (tcgen05 and generic CUDA-core) are held to the same reference tolerance on shards
+    large enough for the tcgen05 kernels; fit_worker asserts which kernels each arm actually ran."""
     case = C.CASES_BY_NAME[name]
-    _compare(case, _run(case, force_generic=True))
-    _compare(case, _run(case, force_generic=False))
+    gen = _run(case, force_generic=True)
+    assert gen[0]['tc_passes'] == 0 and gen[0]['generic_passes'] > 0
+    _compare(case, gen)
+    tc = _run(case, force_generic=False)
+    assert tc[0]['generic_passes'] == 0 and tc[0]['tc_passes'] > 0
+    _compare(case, tc)
 
 
 def test_matches_oracle_live():

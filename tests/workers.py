@@ -101,8 +101,20 @@ def fit_worker(rank, world, case, force_generic=False, resident=True):
         dop = data_operations(A_ij, args)
         ml, nl = (dop.params.m_loc, dop.params.n_loc) if args.topo == '2d' else A_ij.shape
         factors = list(C.draw_given_factors(case, np.random, ml, nl))
+    L.pass_count(True, reset=True)
+    L.pass_count(False, reset=True)
     W, H, err = PyNMF(A_ij, factors=factors, params=args).fit()
+    n_tc, n_generic = L.pass_count(True), L.pass_count(False)
+    if case.get('expect_tc'):
+        # the large cases exist to pin the tcgen05 kernels: every A-streaming pass must have taken that path
+        # (or, in the forced-generic arm of the A/B test, none of them)
+        if force_generic:
+            assert n_tc == 0 and n_generic > 0, 'forced-generic arm ran %d tcgen05 passes' % n_tc
+        else:
+            assert n_generic == 0 and n_tc > 0, '%s: %d passes fell back to the generic kernels (tcgen05: %d)' % (
+                case['name'], n_generic, n_tc)
     out = dict(W=np.asarray(W), H=np.asarray(H), err=float(err), err_dtype=str(np.asarray(err).dtype),
+               tc_passes=int(n_tc), generic_passes=int(n_generic),
                geom=[int(v) for v in (args.m, args.n, args.m_loc, args.n_loc, args.W_start, args.W_end,
                                       args.H_start, args.H_end)])
     if case['prune']:

@@ -197,6 +197,137 @@ __global__ void __launch_bounds__(128, 1) bench_c(int n, int nc, int groups, lon
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+
+// TMEM load / store throughput: `nw` warps (each on its own lane quarter = warp % 4) issue `iters` x32 loads or stores
+// back to back (op 0: tcgen05.ld.32x32b.x32, 1: tcgen05.st.32x32b.x32, 2: ld then st alternating); optionally warp 15
+// keeps the tensor pipe busy with dependent TS MMAs (N = 32) at the same time.
+__global__ void __launch_bounds__(512, 1) bench_tmem(int nw, int op, int iters, int with_mma, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  __shared__ long long cyc[16];
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 512) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tslot;
+  if (warp < nw) {
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+    uint32_t r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = j + threadIdx.x;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (op == 0 || op == 2) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+            "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr + (uint32_t)((i & 1) * 32)) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
+      if (op == 1 || op == 2) {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+            "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+            ::"r"(taddr + (uint32_t)((i & 1) * 32)), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+              "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+              "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+              "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+    }
+    const long long t1 = clock64();
+    uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x ^= r[j];
+    if ((threadIdx.x & 31) == 0) cyc[warp] = (t1 - t0) + (x == 0x12345u ? 1 : 0);
+  } else if (warp == 15 && with_mma) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | (8u << 24);
+    const uint64_t bdesc = make_desc(base + 16384);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters * 4; ++i) mma_ts_elect(tmem + 256u, tmem + 448u, bdesc, idesc, 1u);
+    commit_elect(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    if ((threadIdx.x & 31) == 0) cyc[15] = clock64() - t0;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long mx = 0;
+    for (int w = 0; w < nw; ++w) mx = cyc[w] > mx ? cyc[w] : mx;
+    out[0] = mx;
+    out[1] = with_mma ? cyc[15] : 0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// the KL kernel's tensor work per tile, two issuing warps on independent accumulators: warp 1 = GEMM-2 pattern
+// (4 x {N=64, N=32} dependent), warp 2 = GEMM-1 pattern, either the same 4 x {64, 32} (cat = 0) or 12 x N=32 into one
+// accumulator (cat = 1).  Reports cycles per "tile" (one group from each warp).
+__global__ void __launch_bounds__(128, 1) bench_kl_pattern(int cat, int two_warps, int groups, long long* out) {
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tslot;
+  __shared__ long long cyc[4];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar[0]), 1); mbar_init(smem_u32(&bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tslot;
+  const uint32_t id64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
+  const uint32_t id32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | (8u << 24);
+  if (warp == 1 || (warp == 2 && two_warps)) {
+    const uint64_t bdesc = make_desc(base + 16384 + (warp == 2 ? 8192 : 0));
+    const uint32_t d = tmem + (warp == 2 ? 128u : 0u), a = tmem + (warp == 2 ? 448u : 384u);
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      if (warp == 2 && cat) {
+#pragma unroll
+        for (int kk = 0; kk < 12; ++kk) mma_ts_elect(d, a + (kk & 3) * 8 + (kk >= 8 ? 32 : 0), bdesc + 2 * (kk & 3) + (kk >= 4 && kk < 8 ? 256 : 0), id32, 1u);
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          mma_ts_elect(d, a + kk * 8, bdesc + 2 * kk, id64, 1u);
+          mma_ts_elect(d + 32, a + 32 + kk * 8, bdesc + 2 * kk, id32, 1u);
+        }
+      }
+      commit_elect(smem_u32(&bar[warp - 1]));     // per-tile commit like the kernel (never waited on except at the end)
+    }
+    // drain: wait for the final phase of this warp's barrier
+    mbar_wait(smem_u32(&bar[warp - 1]), (groups - 1) & 1);
+    if ((threadIdx.x & 31) == 0) cyc[warp] = clock64() - t0;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = cyc[1]; out[1] = two_warps ? cyc[2] : 0; }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 template <int KIND>  // 0 tf32, 1 f16
 __global__ void __launch_bounds__(128, 1) bench(int n, int ts, int iters, int nacc, long long* out) {
   extern __shared__ uint8_t smem_raw[];
@@ -307,5 +438,28 @@ int main() {
           printf("  M=%-4d N=%-3d mma=%d commit=%d : %8.1f cyc/group  %6.1f cyc/slot %s\n", m, n, nm, nc, (double)h[0] / 500,
                  (double)h[0] / 500 / (nm + nc), e == cudaSuccess ? "" : cudaGetErrorString(e));
         }
+  cudaFuncSetAttribute(bench_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  printf("TMEM x32 load/store (32 lanes x 32 columns x 4 B = 4 KB per warp instruction): warps op(0 ld,1 st,2 ld+st) mma -> cycles per iteration, B/clk/SM\n");
+  for (int with_mma : {0, 1})
+    for (int op : {0, 1, 2})
+      for (int nw : {1, 4, 8}) {
+        bench_tmem<<<1, 512, 64 * 1024>>>(nw, op, 2000, with_mma, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[2] = {0, 0};
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        const double cyc = (double)h[0] / 2000;
+        printf("  warps=%d op=%d mma=%d : %8.1f cyc/iter  %8.1f B/clk  (mma warp: %.1f cyc per N=32 MMA) %s\n", nw, op, with_mma, cyc,
+               nw * 4096.0 * (op == 2 ? 2 : 1) / cyc, with_mma ? (double)h[1] / 8000 : 0.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
+      }
+  cudaFuncSetAttribute(bench_kl_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  printf("KL tensor work per tile (tf32 TS): cat two_warps -> cycles per tile (warp1, warp2)\n");
+  for (int two : {0, 1})
+    for (int cat : {0, 1}) {
+      bench_kl_pattern<<<1, 128, 64 * 1024>>>(cat, two, 1000, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long h[2] = {0, 0};
+      cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+      printf("  cat=%d two_warps=%d : %8.1f  %8.1f %s\n", cat, two, (double)h[0] / 1000, (double)h[1] / 1000, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    }
   return 0;
 }
