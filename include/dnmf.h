@@ -35,6 +35,7 @@ extern "C" {
 
 #define DNMF_F32 0
 #define DNMF_F64 1
+#define DNMF_I64 2   /* collectives only (prune counts, utils.py:122-126) */
 
 #define DNMF_MATH_ACCURATE 0
 #define DNMF_MATH_TF32 1
@@ -43,6 +44,7 @@ extern "C" {
 #define DNMF_E_UNSUPPORTED (-2) /* k > DNMF_MAX_K or unsupported combination */
 #define DNMF_E_WORKSPACE (-3) /* workspace too small */
 #define DNMF_E_NOGPU (-4)     /* no sm_100 device */
+#define DNMF_E_COMM (-5)      /* NCCL / peer-memory failure */
 
 #define DNMF_MAX_K 64
 
@@ -72,6 +74,8 @@ int dnmf_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int dnmf_set_force_generic(int on);
 /* smallest shard (m*n elements) routed to the tcgen05 path; default 2^20, tests lower it */
 int dnmf_set_tc_min_elems(int64_t elems);
+/* debug: timing-ablation bits of the tcgen05 kernels (tools/prof_tc.py); non-zero values give WRONG results */
+int dnmf_set_tc_debug(int flags);
 /* debug/profiling: device buffer of [n_sm][16] uint64 cycle counters filled by the tcgen05 kernels (NULL = off) */
 int dnmf_set_tc_profile(void* device_buf);
 
@@ -265,6 +269,54 @@ int dnmf_mu_fit_resident_cluster_size(int64_t m, int64_t n, int64_t k, int kl, i
 int dnmf_mu_fit_resident(const void* const* A_ptrs, int64_t lda, void* const* W_ptrs, void* const* H_ptrs, int64_t batch,
                          int64_t m, int64_t n, int64_t k, int kl, int w_update, int64_t it_begin, int64_t it_end,
                          double eps, int dtype, void* stream);
+
+/* ---- communicators: dist_comm.py:16-56 (MPI_comm: world + row / column sub-communicators) as NCCL communicators
+ * owned by this library, one process per GPU.  The 128-byte id is created on one rank (dnmf_comm_unique_id) and
+ * handed to the others by the launcher's own plumbing (torch.distributed object broadcast, a file, MPI ...).
+ * Collectives are SUM reductions / plain copies on DEVICE buffers, in place where MPI's allreduce is
+ * (dist_nmf.py:114, :681, :707, utils.py:122-126), enqueued on `stream` (capturable into a CUDA graph).
+ * dtype: DNMF_F32 / DNMF_F64 / DNMF_I64.  Counts are elements.
+ *   dnmf_allreduce       comm.allreduce(x)                              dist_nmf.py:114,681,707,799; pyDNMF.py:217
+ *   dnmf_allgather       comm.allgather(x) of equal shards, rank order  dist_nmf.py:163,195,284,288
+ *   dnmf_reduce_scatter  comm.Reduce_scatter(send, recv, op=SUM)        dist_nmf.py:169,202,315,341
+ *   dnmf_bcast           comm.bcast(x, root)                            pyDNMF.py:121,129
+ *   dnmf_comm_split      Cart_sub / Split (color, key)                  dist_comm.py:34,48
+ */
+int dnmf_comm_load(const char* libnccl_path);      /* optional: where libnccl.so.2 lives (default: already-loaded copy) */
+int dnmf_comm_nccl_version(int* version);
+int dnmf_comm_unique_id(void* id_out_128);
+int dnmf_comm_init_rank(const void* id_128, int nranks, int rank, void** comm_out);   /* uses the current device */
+int dnmf_comm_split(void* comm, int color, int key, void** comm_out);                /* color < 0: not a member */
+int dnmf_comm_rank(void* comm, int* rank, int* size);
+int dnmf_comm_destroy(void* comm);
+int dnmf_allreduce(void* comm, void* buf, int64_t count, int dtype, void* stream);
+int dnmf_allgather(void* comm, const void* send, void* recv, int64_t count_per_rank, int dtype, void* stream);
+int dnmf_reduce_scatter(void* comm, const void* send, void* recv, int64_t recv_count, int dtype, void* stream);
+int dnmf_bcast(void* comm, void* buf, int64_t count, int dtype, int root, void* stream);
+int dnmf_group_start(void);
+int dnmf_group_end(void);
+
+/* ---- peer-mapped device memory (NVLink / NVSwitch): the one place the library allocates device memory, because the
+ * allocation has to be exportable.  dnmf_symm_alloc returns a zero-filled buffer and its 64-byte CUDA IPC handle;
+ * every other rank of the node maps it with dnmf_symm_open and may then load / store through the returned pointer. */
+int dnmf_symm_alloc(int64_t bytes, void** ptr, void* handle_out_64);
+int dnmf_symm_open(const void* handle_64, void** ptr);
+int dnmf_symm_close(void* ptr);
+int dnmf_symm_free(void* ptr);
+
+/* ---- fused H half-step of the P x 1 row grid over peer memory.
+ * Replaces, per iteration: allreduce(W^T W) dist_nmf.py:679-681, allreduce(W^T A) :705-708, and the update :750-751
+ * (FRO-MU), :832-849 (KL-MU: allreduce of colsum(W) :797-799 and of W^T U :808), :895-913 (FRO-HALS) by
+ * push (reduce-scatter of the partial into the column-chunk owners) -> update of the owned columns from the sum over
+ * ranks in rank order -> write of the new columns into every replica (all-gather); three launches, no NCCL call.
+ *   bases[q]: rank q's exchange region (dnmf_xchg_bytes bytes from dnmf_symm_alloc) as mapped on this rank
+ *   Yt:  this rank's partial (W_i^T A_i)^T, n x k;  aux: its k x k Gram W_i^T W_i (mode 0, 2) or colsum(W_i) (mode 3)
+ *   mode 0 FRO-MU, 2 FRO-HALS, 3 KL-MU;  p0 = eps;  H (k x n) is the replica of this rank, updated in place.
+ * dnmf_xchg_error reads the region's error word (set when a wait for a peer timed out). */
+int64_t dnmf_xchg_bytes(int nranks, int64_t n, int64_t k, int dtype);
+int dnmf_xchg_update_h(void* const* bases, int nranks, int me, int mode, void* H, int64_t ldh, const void* Yt, int64_t ldy,
+                       const void* aux, int64_t n, int64_t k, double p0, int clamp, int dtype, void* stream);
+int dnmf_xchg_error(const void* local_region, int* error_out, void* stream);
 
 #ifdef __cplusplus
 }

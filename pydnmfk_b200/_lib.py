@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DNMF_LIB_PATH') or os.path.join(_HERE, 'libdnmf.so')   # override: A/B builds only
 
-F32, F64 = 0, 1
+F32, F64, I64 = 0, 1, 2
 MATH_ACCURATE, MATH_TF32 = 0, 1
 OP_AH, OP_WTA, OP_KL_UHT, OP_KL_WTU, OP_GRAM, OP_RESIDUAL, OP_SUMS, OP_NNZ = range(8)
 MAX_K = 64
@@ -28,6 +28,7 @@ SIGNATURES = {
     'dnmf_set_force_generic': (i32, [i32]),
     'dnmf_set_tc_min_elems': (i32, [i64]),
     'dnmf_set_tc_profile': (i32, [vp]),
+    'dnmf_set_tc_debug': (i32, [i32]),
     'dnmf_workspace_bytes': (i64, [i32, i64, i64, i64, i32]),
     'dnmf_ah': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, i32, vp, i64, vp]),
     'dnmf_wta': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, i32, i32, vp, i64, vp]),
@@ -72,13 +73,34 @@ SIGNATURES = {
     'dnmf_div_store': (i32, [vp, vp, vp, i64, i64, vp]),
     'dnmf_posneg_colsumsq': (i32, [vp, i64, i64, i64, vp, vp]),
     'dnmf_nnsvd_pick': (i32, [vp, i64, i64, i64, vp, vp, vp, i64, i32, vp]),
+    # communicators (NCCL owned by the library), peer-mapped memory, fused half-step exchange
+    'dnmf_comm_load': (i32, [C.c_char_p]),
+    'dnmf_comm_nccl_version': (i32, [C.POINTER(i32)]),
+    'dnmf_comm_unique_id': (i32, [vp]),
+    'dnmf_comm_init_rank': (i32, [vp, i32, i32, C.POINTER(vp)]),
+    'dnmf_comm_split': (i32, [vp, i32, i32, C.POINTER(vp)]),
+    'dnmf_comm_rank': (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+    'dnmf_comm_destroy': (i32, [vp]),
+    'dnmf_allreduce': (i32, [vp, vp, i64, i32, vp]),
+    'dnmf_allgather': (i32, [vp, vp, vp, i64, i32, vp]),
+    'dnmf_reduce_scatter': (i32, [vp, vp, vp, i64, i32, vp]),
+    'dnmf_bcast': (i32, [vp, vp, i64, i32, i32, vp]),
+    'dnmf_group_start': (i32, []),
+    'dnmf_group_end': (i32, []),
+    'dnmf_symm_alloc': (i32, [i64, C.POINTER(vp), vp]),
+    'dnmf_symm_open': (i32, [vp, C.POINTER(vp)]),
+    'dnmf_symm_close': (i32, [vp]),
+    'dnmf_symm_free': (i32, [vp]),
+    'dnmf_xchg_bytes': (i64, [i32, i64, i64, i32]),
+    'dnmf_xchg_error': (i32, [vp, C.POINTER(i32), vp]),
+    'dnmf_xchg_update_h': (i32, [C.POINTER(vp), i32, i32, i32, vp, i64, vp, i64, vp, i64, i64, dbl, i32, i32, vp]),
     'dnmf_mu_fit_resident_smem_bytes': (i64, [i64, i64, i64, i32, i32]),
     'dnmf_mu_fit_resident_cluster_size': (i32, [i64, i64, i64, i32, i32]),
     'dnmf_mu_fit_resident': (i32, [vp, i64, vp, vp, i64, i64, i64, i64, i32, i32, i64, i64, dbl, i32, vp]),
 }
 
-_NO_STATUS = {'dnmf_pass_count', 'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
-              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile', 'dnmf_colsum_workspace_bytes',
+_NO_STATUS = {'dnmf_xchg_bytes', 'dnmf_pass_count', 'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
+              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile', 'dnmf_set_tc_debug', 'dnmf_colsum_workspace_bytes',
               'dnmf_matvec_workspace_bytes', 'dnmf_mu_fit_resident_smem_bytes', 'dnmf_mu_fit_resident_cluster_size'}
 
 

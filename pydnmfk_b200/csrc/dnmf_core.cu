@@ -88,6 +88,11 @@ int dnmf_set_tc_profile(void* buf) {
   return 0;
 }
 
+int dnmf_set_tc_debug(int flags) {
+  tc_set_debug(flags);
+  return 0;
+}
+
 int dnmf_set_tc_min_elems(int64_t elems) {
   tc_set_min_elems(elems);
   return 0;

@@ -116,6 +116,11 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       long long tprev = clock64(), t_wait = 0, t_issue = 0, t0 = tprev;
+      // L2 prefetch cursor, pf tiles ahead of the ring's loads
+      const int pf = tc_pf_dist(dbg);
+      TileCursor pc;
+      pc.init(blockIdx.x, gridDim.x, x_blocks, kt_total, kt_per_split, num_units);
+      for (int i = 0; i < pf && pc.valid(); ++i) pc.next();
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int xb = unit % x_blocks, sp = unit / x_blocks;
         const int kt0 = sp * kt_per_split;
@@ -126,6 +131,11 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(a_full(s), Cfg::A_BYTES);
           if (MODE == 0) tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, a_full(s), kt * TC_BK, xb * TC_BM);
           else tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, a_full(s), xb * TC_BM, kt * TC_BK);
+          if (pf > 0 && pc.valid()) {
+            if (MODE == 0) tma_prefetch_2d(&tmA, pc.kt * TC_BK, pc.xb() * TC_BM);
+            else tma_prefetch_2d(&tmA, pc.xb() * TC_BM, pc.kt * TC_BK);
+            pc.next();
+          }
           if (++s == SA) { s = 0; ph ^= 1u; }
           TC_T(t_issue);
         }
@@ -143,6 +153,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kt1 = min(kt_total, kt0 + kt_per_split);
         for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(b_free(s), ph ^ 1u);
+          if (dbg & 0x10000) { mbar_arrive(b_full(s)); if (++s == SB) { s = 0; ph ^= 1u; } continue; }    // ablation: no B traffic
           mbar_expect_tx(b_full(s), Cfg::B_BYTES);
           tma_load_2d(sB0 + s * Cfg::B_BYTES, &tmB, b_full(s), kt * TC_BK, 0);
           if (++s == SB) { s = 0; ph ^= 1u; }
@@ -179,7 +190,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool chunk_end = (in_chunk == chunk - 1) || (kt == kt1 - 1);
           // cols [0,K): Ah*Bh (large term, alone in its accumulator);  cols [K,2K): Ah*Bl + Al*Bh (small terms)
           umma_tile_ts<K>(d_tmem, a_raw, make_smem_desc(sB, 16, 1024), in_chunk > 0 ? 1u : 0u, idesc_full, idesc_half,
-                          t_free(ts), b_free(sb), accf_bar(buf), chunk_end ? 1u : 0u, (dbg & 4) ? 1u : 0u);
+                          t_free(ts), TC_SOFT_FREE ? 0u : b_free(sb), accf_bar(buf), chunk_end ? 1u : 0u, (dbg & 4) ? 1u : 0u);
           TC_T(t_mma);
           if (++ts == NT) { ts = 0; pt ^= 1u; }
           if (++sb == SB) { sb = 0; pb ^= 1u; }
@@ -214,14 +225,14 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u;
         mbar_wait(a_full(sa), pa);
         TC_T(t_afull);
-        const uint8_t* tile = base_ptr + sa * Cfg::A_BYTES;
+        const uint8_t* tile_smem = base_ptr + sa * Cfg::A_BYTES;
         uint32_t raw[32], lo[32];
         if (dbg & 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) raw[j] = 0;
         } else if (MODE == 0) {
           // row r = 128 contiguous bytes, 16-byte chunk c stored at position c ^ (r & 7)  (SWIZZLE_128B)
-          const uint8_t* row = tile + r * 128;
+          const uint8_t* row = tile_smem + r * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint4 v = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
@@ -229,10 +240,18 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {
           // [32 K rows][128 columns] row-major: one coalesced 32-bit load per K row
-          const uint8_t* col = tile + r * 4;
+          const uint8_t* col = tile_smem + r * 4;
 #pragma unroll
           for (int j = 0; j < 32; ++j) raw[j] = *reinterpret_cast<const uint32_t*>(col + j * 512);
         }
+#if TC_EARLY_RELEASE
+        {
+          // every register of the tile has arrived (xor_all reads them all): the smem slot goes back to TMA now
+          const uint32_t x = xor_all(raw);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_free(sa) + (x & ((uint32_t)dbg & 0x40000000u)));
+        }
+#endif
         // a - hi(a) is exact; rounding it to tf32 here (nearest) instead of letting the tensor core truncate it
         // removes the one-sided error of the third term
 #pragma unroll
@@ -242,17 +261,23 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         TC_T(t_load);
         mbar_wait(t_free(ts), pt ^ 1u);
         TC_T(t_tfree);
+#if TC_SOFT_FREE
+        // the MMAs of tile (tile - NT) have completed (this operand slot is free again): so is that tile's B slot
+        if (q == 0 && lane == 0 && tile >= NT) mbar_arrive(b_free((tile - NT) % SB));
+#endif
         tc_fence_after();
         if (!(dbg & 1)) {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::OP_COL0 + ts * 64);
           tmem_st_x32(taddr, raw);
           tmem_st_x32(taddr + 32, lo);
         }
+#if !TC_EARLY_RELEASE
         // Release the smem slot only now: the tcgen05.st instructions above consume every loaded register, so all
         // shared-memory loads of this tile have completed (an arrive placed right after the loads could overtake
         // loads still in flight and let TMA overwrite the tile under them).
         __syncwarp();
         if (lane == 0) mbar_arrive(a_free(sa));
+#endif
         if (!(dbg & 1)) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -443,8 +468,7 @@ int launch_pass(const CUtensorMap& tmA, const CUtensorMap& tmB, float* P, int64_
     attr_set = true;
   }
   kern<<<pl.grid, TcCfg<K>::THREADS, TcCfg<K>::SMEM_BYTES, st>>>(tmA, tmB, P, split_stride, x_len, pl.x_blocks, pl.kt_total,
-                                                            pl.kt_per_split, pl.num_units, hi_mode,
-                                                            getenv("DNMF_TC_DBG") ? atoi(getenv("DNMF_TC_DBG")) : 0, g_prof);
+                                                            pl.kt_per_split, pl.num_units, hi_mode, tc_dbg_flags(), g_prof);
   DNMF_LAUNCH_CHECK("tc_pass_kernel");
   return 0;
 }
@@ -571,7 +595,14 @@ int tc_make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, 
 }
 int tc_hi_mode() { return g_hi_mode; }
 unsigned long long* tc_prof_ptr() { return g_prof; }
-int tc_dbg_flags() { return getenv("DNMF_TC_DBG") ? atoi(getenv("DNMF_TC_DBG")) : 0; }
+namespace {
+int g_dbg = -1;       // timing-ablation bits of the tcgen05 kernels (0 in production)
+}
+int tc_dbg_flags() {
+  if (g_dbg < 0) { const char* e = getenv("DNMF_TC_DBG"); g_dbg = e ? (atoi(e) & 0x3FFFFFFF) : 0; }    // read once
+  return g_dbg;
+}
+void tc_set_debug(int flags) { g_dbg = flags < 0 ? 0 : (flags & 0x3FFFFFFF); }
 void tc_launch_split_h(const float* H, int64_t ldh, float* Bcat, int64_t ldb, int k, int kp, int64_t n, cudaStream_t st) {
   tc_split_h_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(H, ldh, Bcat, ldb, k, kp, n);
   tls().launches++;

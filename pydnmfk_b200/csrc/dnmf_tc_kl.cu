@@ -27,17 +27,37 @@ constexpr int KK = 32;            // factor width handled by this kernel
 constexpr int KL_THREADS = 512;
 constexpr int KL_CHUNK = 4;       // K-tiles accumulated in TMEM before the drain warps fold them into registers
 
+// KL_S1 = 1: GEMM1 adds its three split terms into ONE 32-column accumulator (umma_tile_cat); the splitters then load
+// 32 S columns per row instead of 64 and skip an addition, and the freed tensor-memory columns deepen the rings.
+#ifndef KL_S1
+#define KL_S1 0       // measured slower on B200 (12 N=32 MMAs cost more tensor-pipe time than 4 x {N=64, N=32})
+#endif
+
 struct KlCfg {
   static constexpr int N2 = 2 * KK;                    // 64
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;    // 16 KB
   static constexpr int B_BYTES = N2 * TC_BK * 4;       // 8 KB  Bcat tile  [2k][32 r]
   static constexpr int F_BYTES = N2 * KK * 4;          // 8 KB  FrCat tile [hi 32 r | lo 32 r][k]
-  static constexpr int SA = 6, SB = 6, SF = 6;
-  static constexpr int NBUF = 2, NT = 2, NS = 3;
+#ifndef KL_SA
+#define KL_SA 8
+#define KL_SB 4
+#define KL_SF 4
+#endif
+  static constexpr int SA = KL_SA, SB = KL_SB, SF = KL_SF;
+#if KL_S1
+  static constexpr int NBUF = 2, NT = 3, NS = 4, S_COLS = KK;
+#else
+#ifndef KL_NT
+#define KL_NBUF 2
+#define KL_NT 2
+#define KL_NS 3
+#endif
+  static constexpr int NBUF = KL_NBUF, NT = KL_NT, NS = KL_NS, S_COLS = 2 * KK;
+#endif
   static constexpr int ACC_COL0 = 0;
   static constexpr int OP_COL0 = NBUF * N2;            // 128
-  static constexpr int S_COL0 = OP_COL0 + NT * 64;     // 256
-  static constexpr int FX_COL0 = S_COL0 + NS * 64;     // 448
+  static constexpr int S_COL0 = OP_COL0 + NT * 64;
+  static constexpr int FX_COL0 = S_COL0 + NS * S_COLS; // 448
   static_assert(FX_COL0 + 64 <= 512, "TMEM has 512 columns");
   static constexpr int NBARS = 2 * SA + 2 * SB + 2 * SF + 2 * NT + 2 * NS + 2 * NBUF + 2;
   static constexpr int BAR_BYTES = 1024;
@@ -53,7 +73,10 @@ __global__ void __launch_bounds__(KL_THREADS, 1)
 tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmF, const float* __restrict__ Fx, int64_t ldfx, int64_t fr_rows_pad,
              float* __restrict__ P, int64_t split_stride, int64_t x_len, int x_blocks, int kt_total, int kt_per_split,
-             int num_units, int k_real, float eps, unsigned long long* __restrict__ prof) {
+             int num_units, int k_real, float eps, int dbg, unsigned long long* __restrict__ prof) {
+  // dbg (dnmf_set_tc_debug, timing ablations only -- results become wrong): 1 skip the division, 2 skip the S load,
+  // 4 skip the GEMM1 MMAs, 8 skip the GEMM2 low-order MMAs, 16 skip all GEMM2 MMAs, 32 skip the U split, 64 skip the
+  // shared-memory read of the A tile, 0x10000 skip the Bcat TMA loads, 0x20000 skip the FrCat TMA loads
   using Cfg = KlCfg;
   constexpr int SA = Cfg::SA, SB = Cfg::SB, SF = Cfg::SF, NT = Cfg::NT, NS = Cfg::NS, NBUF = Cfg::NBUF, N2 = Cfg::N2;
   extern __shared__ uint8_t smem_raw[];
@@ -102,6 +125,10 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      const int pf = tc_pf_dist(dbg);            // L2 prefetch cursor, pf tiles ahead of the ring's loads (tc_common.cuh)
+      TileCursor pc;
+      pc.init(blockIdx.x, gridDim.x, x_blocks, kt_total, kt_per_split, num_units);
+      for (int i = 0; i < pf && pc.valid(); ++i) pc.next();
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int xb = unit % x_blocks, sp = unit / x_blocks;
         const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
@@ -110,6 +137,11 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_expect_tx(bar(iAF + s), Cfg::A_BYTES);
           if (MODE != 1) tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, bar(iAF + s), kt * TC_BK, xb * TC_BM);
           else tma_load_2d(sA0 + s * Cfg::A_BYTES, &tmA, bar(iAF + s), xb * TC_BM, kt * TC_BK);
+          if (pf > 0 && pc.valid()) {
+            if (MODE != 1) tma_prefetch_2d(&tmA, pc.kt * TC_BK, pc.xb() * TC_BM);
+            else tma_prefetch_2d(&tmA, pc.xb() * TC_BM, pc.kt * TC_BK);
+            pc.next();
+          }
           if (++s == SA) { s = 0; ph ^= 1u; }
         }
       }
@@ -124,6 +156,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
         for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(bar(iBE + s), ph ^ 1u);
+          if (dbg & 0x10000) { mbar_arrive(bar(iBF + s)); if (++s == SB) { s = 0; ph ^= 1u; } continue; }   // ablation
           mbar_expect_tx(bar(iBF + s), Cfg::B_BYTES);
           tma_load_2d(sB0 + s * Cfg::B_BYTES, &tmB, bar(iBF + s), kt * TC_BK, 0);
           if (++s == SB) { s = 0; ph ^= 1u; }
@@ -138,6 +171,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
         for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(bar(iFE + s), ph ^ 1u);
+          if (dbg & 0x20000) { mbar_arrive(bar(iFF + s)); if (++s == SF) { s = 0; ph ^= 1u; } continue; }   // ablation
           mbar_expect_tx(bar(iFF + s), Cfg::F_BYTES);
           tma_load_2d(sF0 + s * Cfg::F_BYTES, &tmF, bar(iFF + s), 0, kt * TC_BK);
           tma_load_2d(sF0 + s * Cfg::F_BYTES + Cfg::F_BYTES / 2, &tmF, bar(iFF + s), 0, (int)fr_rows_pad + kt * TC_BK);
@@ -147,9 +181,11 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 15) {
     // ===================== GEMM1 issuer: S = Fx . Fr^T, runs ahead of GEMM2 by up to NS tiles =====================
-    //   cols [0,32) Fx_hi*Fr_hi ; cols [32,64) Fx_hi*Fr_lo + Fx_lo*Fr_hi
+    //   KL_S1: cols [0,32) = Fx_hi*Fr_hi + Fx_hi*Fr_lo + Fx_lo*Fr_hi
+    //   else : cols [0,32) Fx_hi*Fr_hi ; cols [32,64) Fx_hi*Fr_lo + Fx_lo*Fr_hi
     constexpr uint32_t idesc_full = make_idesc(N2, 0);
     constexpr uint32_t idesc_half = make_idesc(KK, 0);
+    (void)idesc_full;
     int sf = 0, ss = 0;
     uint32_t pf = 0, ps = 0, pxu = 0;
     const uint32_t fx_tmem = tmem_base + (uint32_t)Cfg::FX_COL0;
@@ -164,9 +200,19 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(bar(iSE + ss), ps ^ 1u);
         TC_T(t_g1wait);
         tc_fence_after();
-        umma_tile_ts<KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * 64), fx_tmem,
-                         make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), 0u, idesc_full, idesc_half,
-                         bar(iSF + ss), bar(iFE + sf), bar(iXE), (j == ntiles - 1) ? 1u : 0u, 0u);
+        if (dbg & 4)
+          umma_commits_only(bar(iSF + ss), bar(iFE + sf), bar(iXE), (j == ntiles - 1) ? 1u : 0u);
+        else
+#if KL_S1
+          umma_tile_cat<KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS), fx_tmem,
+                            make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), idesc_half,
+                            bar(iSF + ss), bar(iFE + sf), bar(iXE), (j == ntiles - 1) ? 1u : 0u);
+#else
+          umma_tile_ts<KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS), fx_tmem,
+                           make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), 0u, idesc_full, idesc_half,
+                           bar(iSF + ss), (TC_SOFT_FREE && !KL_S1) ? 0u : bar(iFE + sf), bar(iXE),
+                           (j == ntiles - 1) ? 1u : 0u, 0u);
+#endif
         if (++sf == SF) { sf = 0; pf ^= 1u; }
         if (++ss == NS) { ss = 0; ps ^= 1u; }
         __syncwarp();
@@ -196,9 +242,13 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         TC_T(t_bfull);
         tc_fence_after();
         const bool chunk_end = (in_chunk == KL_CHUNK - 1) || (i == ntiles - 1);
-        umma_tile_ts<KK>(tmem_base + (uint32_t)(Cfg::ACC_COL0 + buf * N2), tmem_base + (uint32_t)(Cfg::OP_COL0 + ts * 64),
-                         make_smem_desc(sB0 + sb * Cfg::B_BYTES, 16, 1024), in_chunk > 0 ? 1u : 0u, idesc_full, idesc_half,
-                         bar(iTE + ts), bar(iBE + sb), bar(iCF + buf), chunk_end ? 1u : 0u, 0u);
+        if (dbg & 16)
+          umma_commits_only(bar(iTE + ts), bar(iBE + sb), bar(iCF + buf), chunk_end ? 1u : 0u);
+        else
+          umma_tile_ts<KK>(tmem_base + (uint32_t)(Cfg::ACC_COL0 + buf * N2), tmem_base + (uint32_t)(Cfg::OP_COL0 + ts * 64),
+                           make_smem_desc(sB0 + sb * Cfg::B_BYTES, 16, 1024), in_chunk > 0 ? 1u : 0u, idesc_full, idesc_half,
+                           bar(iTE + ts), (TC_SOFT_FREE && MODE != 2) ? 0u : bar(iBE + sb), bar(iCF + buf),
+                           chunk_end ? 1u : 0u, (dbg & 8) ? 1u : 0u);
         if (++ts == NT) { ts = 0; pt ^= 1u; }
         if (++sb == SB) { sb = 0; pb ^= 1u; }
         if (chunk_end) { if (++buf == NBUF) { buf = 0; accphase ^= 1u; } }
@@ -254,7 +304,10 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         TC_T(t_afull);
         const uint8_t* tl = base_ptr + sa * Cfg::A_BYTES;
         uint32_t u[32], lo[32];
-        if (MODE != 1) {
+        if (dbg & 64) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) u[j] = 0x3F800000u + (uint32_t)(j + lane);
+        } else if (MODE != 1) {
           const uint8_t* row = tl + r * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -266,24 +319,49 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int j = 0; j < 32; ++j) u[j] = *reinterpret_cast<const uint32_t*>(col + j * 512);
         }
+#if TC_EARLY_RELEASE
+        if (MODE != 2) {
+          // every register of the tile has arrived (xor_all reads them all): the smem slot goes back to TMA now
+          const uint32_t x = xor_all(u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(iAE + sa) + (x & ((uint32_t)dbg & 0x40000000u)));
+        }
+#endif
         // S tile of this accumulator row
         TC_T(t_load);
         mbar_wait(bar(iSF + ss), ps);
         TC_T(t_sfull);
+#if TC_SOFT_FREE && !KL_S1
+        // GEMM1 of this tile has completed (it committed to the S barrier): its factor tile may be overwritten
+        if (q == 0 && lane == 0 && !(dbg & 4)) mbar_arrive(bar(iFE + tile % SF));
+#endif
         tc_fence_after();
-        const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::S_COL0 + ss * 64);
+        const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS);
         {
+#if KL_S1
+          uint32_t s0[32];
+          if (dbg & 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s0[j] = 0x3F800000u;
+          } else {
+            tmem_ld_x32(saddr, s0);         // Fx_hi * Fr_hi + Fx_hi * Fr_lo + Fx_lo * Fr_hi
+            tmem_ld_wait();
+          }
+#define KL_S_OF(j) __uint_as_float(s0[j])
+#else
           uint32_t s0[32], s1[32];
           tmem_ld_x32(saddr, s0);           // Fx_hi * Fr_hi
           tmem_ld_x32(saddr + 32, s1);      // Fx_hi * Fr_lo + Fx_lo * Fr_hi
           tmem_ld_wait();
+#define KL_S_OF(j) (__uint_as_float(s0[j]) + __uint_as_float(s1[j]))
+#endif
           if (MODE == 2) {
             // residual: this row's 32 elements of (A - W H)^2 and A^2, fp32 within the tile, float64 across tiles
             float t_res = 0.f, t_a = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float a = __uint_as_float(u[j]);
-              const float d = a - (__uint_as_float(s0[j]) + __uint_as_float(s1[j]));
+              const float d = a - KL_S_OF(j);
               t_res = fmaf(d, d, t_res);
               t_a = fmaf(a, a, t_a);
             }
@@ -299,29 +377,36 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float den = (__uint_as_float(s0[j]) + __uint_as_float(s1[j])) + eps;
+            const float den = KL_S_OF(j) + eps;
             const float a = __uint_as_float(u[j]);
             // den >= eps > 0 and far from overflow: one MUFU.RCP (1 ulp) and one multiply, no range handling.  The
             // rounding errors of the 65536 quotients of a row are independent and average out in the contraction.
-            u[j] = __float_as_uint(a * rcp_approx(den));
+            u[j] = __float_as_uint((dbg & 1) ? a * den : a * rcp_approx(den));
           }
+#undef KL_S_OF
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iSE + ss));          // S slot may be overwritten
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          lo[j] = tf32_lo_bits(u[j]);
+          lo[j] = (dbg & 32) ? u[j] : tf32_lo_bits(u[j]);
         }
         TC_T(t_div);
         mbar_wait(bar(iTE + ts), pt ^ 1u);
         TC_T(t_tfree);
+#if TC_SOFT_FREE
+        // GEMM2 of tile (tile - NT) has completed (this operand slot is free again): so is that tile's Bcat slot
+        if (q == 0 && lane == 0 && tile >= NT && !(dbg & 16)) mbar_arrive(bar(iBE + (tile - NT) % SB));
+#endif
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::OP_COL0 + ts * 64);
         tmem_st_x32(taddr, u);
         tmem_st_x32(taddr + 32, lo);
+#if !TC_EARLY_RELEASE
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iAE + sa));          // smem tile fully consumed (see dnmf_tc.cu)
+#endif
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -520,7 +605,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
     }
     kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmB, tmF, Fx, ldfx, kp.r_pad, P, split_stride, x_len,
                                                           pl.x_blocks, pl.kt_total, pl.kt_per_split, pl.num_units,
-                                                          k_real, eps, tc_prof_ptr());
+                                                          k_real, eps, tc_dbg_flags(), tc_prof_ptr());
     DNMF_LAUNCH_CHECK("tc_kl_kernel");
     return 0;
   };
@@ -580,7 +665,7 @@ int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, co
   // (the GEMM2 operand map is unused in this mode: tmF stands in for it)
   kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmF, tmF, W, ldw, kp.r_pad, reinterpret_cast<float*>(pairs), 0, m,
                                                         pl.x_blocks, pl.kt_total, pl.kt_per_split, pl.num_units, k, 0.f,
-                                                        tc_prof_ptr());
+                                                        0, tc_prof_ptr());
   DNMF_LAUNCH_CHECK("tc_kl_kernel<2>");
   *out_pairs = pairs;
   *n_pairs = (int64_t)pl.grid * 256;

@@ -8,6 +8,7 @@ namespace dnmf {
 // lda % 4 == 0, shard large enough to fill the machine, sm_100 device, and not forced off.
 bool tc_eligible(int op, const void* A, int64_t lda, int64_t m, int64_t n, int64_t k, int dtype);
 void tc_set_min_elems(int64_t elems);
+void tc_set_debug(int flags);      // timing-ablation bits (tests/tools only; results become wrong when non-zero)
 void tc_set_profile(void* buf);   // debug: device buffer [grid][16] of cycle counts per warp role, or nullptr
 int64_t tc_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype);
 

@@ -26,7 +26,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Blocking wait.  try_wait suspends the warp in hardware until the phase completes or a time limit expires; with the
+// default limit the waiting roles (producers, issuers, drain warps) re-issued YIELD / TRYWAIT / BRA triplets often enough
+// to make up 28 % of all executed warp instructions of the KL pass (ncu source page, round 1).  The explicit
+// suspend-time hint keeps a waiting warp parked until the barrier actually flips.
+#ifndef DNMF_WAIT_HINT
+#define DNMF_WAIT_HINT 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if DNMF_WAIT_HINT
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+#else
   uint32_t done;
   do {
     asm volatile(
@@ -37,6 +55,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
+#endif
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -49,6 +68,58 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// DRAM -> L2 only: issued TC_PF tiles ahead of the shared-memory ring so that the ring's own loads find their tile
+// in L2.  The A ring holds 6-9 tiles (96-144 KB) per SM; at the loaded DRAM latency that many bytes in flight cap a
+// pass near 8.7 TB/s of TMA traffic whatever the kernel computes (round-2 ablations: removing every MMA or all of the
+// splitter arithmetic left the pass time unchanged).  Prefetching decouples the DRAM latency from the ring depth.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+#ifndef TC_PF_DEFAULT
+#define TC_PF_DEFAULT 0
+#endif
+// prefetch distance in tiles from the debug word (bits 8-15: 0 = default, v = v - 1 tiles)
+__device__ __forceinline__ int tc_pf_dist(int dbg) {
+  const int v = (dbg >> 8) & 0xFF;
+  return v ? v - 1 : TC_PF_DEFAULT;
+}
+// XOR of a tile row held in registers.  Reading every register makes the warp wait for the shared-memory loads that
+// fill them, so the A slot can be handed back to TMA right afterwards (instead of after the tensor-memory store
+// that consumes the registers much later); the value is folded into the barrier address through a mask that is zero at
+// run time but opaque to the compiler.
+__device__ __forceinline__ uint32_t xor_all(const uint32_t (&r)[32]) {
+  uint32_t x = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x ^= r[j];
+  return x;
+}
+#ifndef TC_EARLY_RELEASE
+#define TC_EARLY_RELEASE 0
+#endif
+
+// (unit, k-tile) sequence of one persistent CTA, used by the producers' prefetch cursor
+struct TileCursor {
+  int unit, kt, kt1;
+  int x_blocks, kt_total, kt_per_split, num_units, stride;
+  __device__ __forceinline__ void init(int first_unit, int stride_, int x_blocks_, int kt_total_, int kt_per_split_, int num_units_) {
+    x_blocks = x_blocks_; kt_total = kt_total_; kt_per_split = kt_per_split_; num_units = num_units_; stride = stride_;
+    unit = first_unit;
+    load_unit();
+  }
+  __device__ __forceinline__ void load_unit() {
+    if (unit < num_units) {
+      const int sp = unit / x_blocks;
+      kt = sp * kt_per_split;
+      kt1 = min(kt_total, kt + kt_per_split);
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return unit < num_units; }
+  __device__ __forceinline__ int xb() const { return unit % x_blocks; }
+  __device__ __forceinline__ void next() {
+    if (++kt >= kt1) { unit += stride; load_unit(); }
+  }
+};
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -93,6 +164,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
       ::"r"(bar) : "memory");
 }
 
+// TC_SOFT_FREE = 1: the B-operand slot of a tile is handed back to its TMA producer by a splitter warp (a plain
+// mbarrier.arrive once it has seen the barrier that the tile's MMAs committed to) instead of by a second
+// tcgen05.commit; every commit costs the tensor pipe's front end ~40 cycles (tools/umma_bench.cu) and the KL pass is
+// bound by that front end (round-2 role timers: both issuers busy 47 % each).  bar_b == 0 skips the commit.
+#ifndef TC_SOFT_FREE
+#define TC_SOFT_FREE 1
+#endif
+
 // One K tile (4 K=8 steps) of the 3-term split, plus the tcgen05.commits that release the operand slot, the B slot
 // and (at a chunk end) the accumulator, issued from ONE asm block under a single elect.sync: the uniform-datapath
 // set-up (ELECT, R2UR of every operand) is paid once per tile instead of once per instruction.
@@ -103,7 +182,7 @@ __device__ __forceinline__ void umma_tile_ts(uint32_t d_tmem, uint32_t a_raw, ui
                                              uint32_t bar_acc, uint32_t chunk_end, uint32_t skip_lo) {
   asm volatile(
       "{\n\t"
-      ".reg .pred q, p0, p1, pc, pl;\n\t"
+      ".reg .pred q, p0, p1, pc, pl, pb;\n\t"
       ".reg .b32 dl, a1, a2, a3, l0, l1, l2, l3;\n\t"
       ".reg .b64 b1, b2, b3;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
@@ -113,6 +192,8 @@ __device__ __forceinline__ void umma_tile_ts(uint32_t d_tmem, uint32_t a_raw, ui
       "and.pred pc, pc, q;\n\t"
       "setp.eq.b32 pl, %10, 0;\n\t"
       "and.pred pl, pl, q;\n\t"
+      "setp.ne.b32 pb, %7, 0;\n\t"
+      "and.pred pb, pb, q;\n\t"
       "add.u32 dl, %0, %11;\n\t"
       "add.u32 l0, %1, 32;\n\t"
       "add.u32 a1, %1, 8;\n\t"
@@ -133,11 +214,80 @@ __device__ __forceinline__ void umma_tile_ts(uint32_t d_tmem, uint32_t a_raw, ui
       "@q  tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], b3, %4, p1;\n\t"
       "@pl tcgen05.mma.cta_group::1.kind::tf32 [dl], [l3], b3, %5, p1;\n\t"
       "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
-      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+      "@pb tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
       "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
       "}\n"
       ::"r"(d_tmem), "r"(a_raw), "l"(bdesc), "r"(acc_first), "r"(idesc_full), "r"(idesc_half), "r"(bar_t), "r"(bar_b),
         "r"(bar_acc), "r"(chunk_end), "r"(skip_lo), "n"(K)
+      : "memory");
+}
+
+// One K tile of the 3-term split K-CONCATENATED into a single accumulator (12 MMAs of N = K):
+//   D[:, 0:K] = A_hi[tmem] * B_hi^T + A_hi * B_lo^T + A_lo[tmem + 32] * B_hi^T
+// B tile = [K hi rows | K lo rows] of 128 bytes (LO_OFF = K * 128 / 16 descriptor units).  Used where an accumulator
+// lives for ONE tile only (the KL path's S = W H): the truncating accumulation of the tensor core then adds 12 terms,
+// far below the bias that made the long-lived accumulators keep the large term apart (see dnmf_tc.cu).
+template <int K>
+__device__ __forceinline__ void umma_tile_cat(uint32_t d_tmem, uint32_t a_hi, uint64_t bdesc, uint32_t idesc_n, uint32_t bar_t,
+                                              uint32_t bar_b, uint32_t bar_acc, uint32_t chunk_end) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q, p0, p1, pc;\n\t"
+      ".reg .b32 a1, a2, a3, l0, l1, l2, l3;\n\t"
+      ".reg .b64 b1, b2, b3, c0, c1, c2, c3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p0, 0, 0;\n\t"
+      "setp.eq.b32 p1, 0, 0;\n\t"
+      "setp.ne.b32 pc, %7, 0;\n\t"
+      "and.pred pc, pc, q;\n\t"
+      "add.u32 a1, %1, 8;\n\t"
+      "add.u32 a2, %1, 16;\n\t"
+      "add.u32 a3, %1, 24;\n\t"
+      "add.u32 l0, %1, 32;\n\t"
+      "add.u32 l1, %1, 40;\n\t"
+      "add.u32 l2, %1, 48;\n\t"
+      "add.u32 l3, %1, 56;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "add.u64 b2, %2, 4;\n\t"
+      "add.u64 b3, %2, 6;\n\t"
+      "add.u64 c0, %2, %8;\n\t"
+      "add.u64 c1, c0, 2;\n\t"
+      "add.u64 c2, c0, 4;\n\t"
+      "add.u64 c3, c0, 6;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [a1], b1, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], b2, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], b3, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], c0, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [a1], c1, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], c2, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], c3, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [l0], %2, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [l1], b1, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [l2], b2, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [l3], b3, %3, p1;\n\t"
+      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t"
+      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "}\n"
+      ::"r"(d_tmem), "r"(a_hi), "l"(bdesc), "r"(idesc_n), "r"(bar_t), "r"(bar_b), "r"(bar_acc), "r"(chunk_end),
+        "n"(K * 8)
+      : "memory");
+}
+
+// the commits of a tile without its MMAs (timing ablations only)
+__device__ __forceinline__ void umma_commits_only(uint32_t bar_t, uint32_t bar_b, uint32_t bar_acc, uint32_t chunk_end) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q, pc;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 pc, %3, 0;\n\t"
+      "and.pred pc, pc, q;\n\t"
+      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t"
+      "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%2];\n\t"
+      "}\n"
+      ::"r"(bar_t), "r"(bar_b), "r"(bar_acc), "r"(chunk_end)
       : "memory");
 }
 

@@ -21,9 +21,24 @@ keeps grid dimension 0, i.e. it spans the p_r ranks of one grid *column*;
 import os
 import time
 
+import ctypes as _C
+import socket
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import _lib as L
+
+_NCCL_DT = {torch.float32: L.F32, torch.float64: L.F64, torch.int64: L.I64}
+_comm_cache = {}       # (member tuple, dims) -> Comm (keeps its library communicator across fits)
+_group_cache = {}      # member tuple -> torch process group (new_group is world-collective: create each one once)
+
+
+def _use_library_nccl():
+    """Device collectives go through the NCCL communicators owned by libdnmf.so (include/dnmf.h, dnmf_comm_*)
+    unless DNMF_TORCH_COLLECTIVES=1 keeps them on torch.distributed's own NCCL process group."""
+    return os.environ.get('DNMF_TORCH_COLLECTIVES', '0') != '1'
 
 
 def _ensure_world():
@@ -64,6 +79,33 @@ class Comm:
         me = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
         self._me = self._ranks.index(me)
         self._subs = {}
+        self._lib_comm = None          # NCCL communicator owned by libdnmf.so, created on first use
+
+    # ---- NCCL communicator inside libdnmf.so (the C-ABI's dnmf_comm_*) ---------------------------
+    def _library_comm(self):
+        """Collective over this communicator on first use: rank 0 creates the 128-byte NCCL id, torch.distributed
+        (plumbing) hands it to the members, every member joins with dnmf_comm_init_rank on its current device."""
+        parent = getattr(self, '_parent', None)
+        if parent is not None:                 # a Cartesian view of the same members
+            return parent._library_comm()
+        if self._lib_comm is None:
+            ident = _C.create_string_buffer(128)
+            if self._me == 0:
+                L.call('dnmf_comm_unique_id', ident)
+            box = [ident.raw]
+            dist.broadcast_object_list(box, src=self._ranks[0], group=self._group, device=self._dev())
+            out = _C.c_void_p()
+            L.call('dnmf_comm_init_rank', _C.create_string_buffer(box[0], 128), self.size, self._me, _C.byref(out))
+            self._lib_comm = out
+        return self._lib_comm
+
+    def _lib_ok(self, t):
+        return (self.backend == 'nccl' and t.is_cuda and t.dtype in _NCCL_DT and t.is_contiguous()
+                and _use_library_nccl())
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
 
     # ---- identity (mpi4py spelling) -------------------------------------------------------
     @property
@@ -102,6 +144,8 @@ class Comm:
             h = t.detach().cpu()
             dist.all_reduce(h, group=self._group)
             t.copy_(h)
+        elif self._lib_ok(t):
+            L.call('dnmf_allreduce', self._library_comm(), t.data_ptr(), t.numel(), _NCCL_DT[t.dtype], self._stream())
         else:
             dist.all_reduce(t, group=self._group)
         return t
@@ -118,6 +162,9 @@ class Comm:
                 ho = out.cpu()
                 dist.all_gather_into_tensor(ho, t.cpu(), group=self._group)
                 out.copy_(ho)
+            elif self._lib_ok(t):
+                L.call('dnmf_allgather', self._library_comm(), t.data_ptr(), out.data_ptr(), t.numel(), _NCCL_DT[t.dtype],
+                       self._stream())
             else:
                 dist.all_gather_into_tensor(out, t, group=self._group)
             return out
@@ -139,7 +186,11 @@ class Comm:
             sizes = [t.shape[0] // self.size] * self.size
         if len(set(sizes)) == 1 and not self._staged(t) and self.backend == 'nccl':
             out = torch.empty((sizes[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            dist.reduce_scatter_tensor(out, t, group=self._group)
+            if self._lib_ok(t):
+                L.call('dnmf_reduce_scatter', self._library_comm(), t.data_ptr(), out.data_ptr(), out.numel(),
+                       _NCCL_DT[t.dtype], self._stream())
+            else:
+                dist.reduce_scatter_tensor(out, t, group=self._group)
             return out
         # ragged shards or gloo: all-reduce, then slice
         full = self.allreduce_(t.clone())
@@ -154,6 +205,8 @@ class Comm:
             h = t.detach().cpu()
             dist.broadcast(h, src=src, group=self._group)
             t.copy_(h)
+        elif self._lib_ok(t):
+            L.call('dnmf_bcast', self._library_comm(), t.data_ptr(), t.numel(), _NCCL_DT[t.dtype], int(root), self._stream())
         else:
             dist.broadcast(t, src=src, group=self._group)
         return t
@@ -234,7 +287,9 @@ class Comm:
     # ---- topology --------------------------------------------------------------------------
     def Create_cart(self, dims, periods=None, reorder=False):
         assert int(np.prod(dims)) == self.size, 'grid %s does not match %d ranks' % (dims, self.size)
-        return Comm(self._ranks, self._group, dims=dims)
+        c = Comm(self._ranks, self._group, dims=dims)
+        c._parent = self                      # same members, same order: share the library communicator
+        return c
 
     def Get_coords(self, rank):
         return [int(c) for c in np.unravel_index(rank, self._dims)]
@@ -257,9 +312,18 @@ class Comm:
             members = [self._ranks[r] for r in buckets[bkey]]
             group = None
             if len(members) > 1 and dist.is_available() and dist.is_initialized():
-                group = dist.new_group(ranks=members)
+                # torch.distributed.new_group is collective over the WHOLE default group: Create_cart / Sub must be
+                # reached by every process in the same order (they are: MPI_comm is built by every rank).  Groups are
+                # cached by member list, so repeated fits re-use them instead of leaking one per MPI_comm.
+                gkey = tuple(members)
+                if gkey not in _group_cache:
+                    _group_cache[gkey] = dist.new_group(ranks=members)
+                group = _group_cache[gkey]
             if bkey == mine:
-                sub = Comm(members, group, dims=[self._dims[d] for d in keep])
+                ckey = (tuple(members), tuple(self._dims[d] for d in keep))
+                if ckey not in _comm_cache:
+                    _comm_cache[ckey] = Comm(members, group, dims=[self._dims[d] for d in keep])
+                sub = _comm_cache[ckey]
         self._subs[key] = sub
         return sub
 
@@ -285,6 +349,8 @@ class _MPI:
 
     def _reset(self):
         self._world = None
+        _comm_cache.clear()
+        _group_cache.clear()
 
     @staticmethod
     def Wtime():

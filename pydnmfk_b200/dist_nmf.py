@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import device as D
+from . import peer
 from .utils import norm, comm_timing, parse, var_init  # noqa: F401  (re-exported like the reference)
 from .dist_comm import MPI  # noqa: F401
 
@@ -325,6 +326,10 @@ class nmf_algorithms_1D(_AlgBase):
         self.A_ij, self.W_i, self.H_j = self._setup(A_ij, W_i, H_j, params)
         self.local_W_m = self.W_i.shape[0]
         self.local_H_n = self.H_j.shape[1]
+        # row grid: the H half-step runs as one exchange over peer memory instead of two all-reduces (peer.py)
+        self._px = None
+        if self.p_c == 1 and self.p_r > 1 and self.comm1.size == self.p_r and self.H_j.stride(1) == 1:
+            self._px = peer.get(self.comm1, self.H_j.shape[1], self.k, self.H_j.dtype)
 
     def _W(self):
         return self.W_i
@@ -384,6 +389,11 @@ class nmf_algorithms_1D(_AlgBase):
     @comm_timing()
     def Fro_MU_update_H(self):
         """dist_nmf.py:735-751."""
+        if self._px is not None:
+            G = self.ops.gram(self.W_i, trans=False)                      # this rank's W_i^T W_i
+            Yt = self.ops.wta(self.A_ij, self.W_i, transposed_out=True)   # this rank's (W_i^T A_i)^T
+            self._px.update_h(0, self.H_j, Yt, G, self.eps)
+            return
         W_TW = self._gram_W(self.W_i)
         AtW, _ = self._WTA(self.W_i)
         self.ops.mu_update_h(self.H_j, AtW, W_TW, self.eps)
@@ -421,6 +431,11 @@ class nmf_algorithms_1D(_AlgBase):
 
     def KL_MU_update_H(self):
         """dist_nmf.py:832-849."""
+        if self._px is not None:
+            x = self.ops.colsum(self.W_i)                                  # this rank's column sums of W_i
+            Yt = self.ops.kl_wtu(self.A_ij, self.W_i, self.H_j, self.eps, transposed_out=True)
+            self._px.update_h(3, self.H_j, Yt, x, self.eps)
+            return
         x2 = self.sum_along_axis(self.W_i, p=self.p_r, axis=0)
         sk = self.glob_UX(axis=1)
         self.ops.kl_update_h(self.H_j, sk, x2, self.eps)
@@ -444,6 +459,11 @@ class nmf_algorithms_1D(_AlgBase):
 
     def FRO_HALS_update_H(self):
         """dist_nmf.py:895-913."""
+        if self._px is not None:
+            G = self.ops.gram(self.W_i, trans=False)
+            Yt = self.ops.wta(self.A_ij, self.W_i, transposed_out=True)
+            self._px.update_h(2, self.H_j, Yt, G, self.eps)
+            return
         WTW = self._gram_W(self.W_i)
         AtW, _ = self._WTA(self.W_i)
         self.ops.hals_h(self.H_j, AtW, WTW, self.eps)

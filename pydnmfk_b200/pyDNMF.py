@@ -180,6 +180,8 @@ class PyNMF():
             if i == self.itr - 1:
                 break
         sg = None                              # drop the captured graphs (and their NCCL nodes) with the loop
+        if getattr(alg, '_px', None) is not None:
+            alg._px.check()                    # a peer that died mid-exchange must not go unnoticed
 
     def _finish(self):
         """What the reference does on the last iteration (pyDNMF.py:158-166,173-181): normalise, relative error,

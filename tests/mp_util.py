@@ -22,7 +22,7 @@ def _free_port():
     return port
 
 
-def _entry(rank, world, port, backend, fn, args, outdir):
+def _entry(rank, world, port, backend, fn, args, outdir, env=None):
     os.environ['RANK'] = str(rank)
     os.environ['LOCAL_RANK'] = '0'
     os.environ['WORLD_SIZE'] = str(world)
@@ -31,6 +31,8 @@ def _entry(rank, world, port, backend, fn, args, outdir):
     os.environ['DNMF_BACKEND'] = backend
     os.environ['OMP_NUM_THREADS'] = '1'
     os.environ.setdefault('DNMF_PG_TIMEOUT_S', '240')
+    for key, val in (env or {}).items():
+        os.environ[key] = str(val)
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     try:
@@ -48,11 +50,11 @@ def _entry(rank, world, port, backend, fn, args, outdir):
         pass
 
 
-def run(world, fn, args=(), backend='gloo', timeout=600):
+def run(world, fn, args=(), backend='gloo', timeout=600, env=None):
     """Returns [fn(rank, world, *args) for every rank]; raises if any rank failed."""
     outdir = tempfile.mkdtemp(prefix='dnmf_mp_')
     port = _free_port()
-    ctx = mp.start_processes(_entry, args=(world, port, backend, fn, args, outdir), nprocs=world, join=False,
+    ctx = mp.start_processes(_entry, args=(world, port, backend, fn, args, outdir, env), nprocs=world, join=False,
                              start_method='spawn')
     ctx.join(timeout)
     for p in ctx.processes:

@@ -103,7 +103,8 @@ def fit_worker(rank, world, case, force_generic=False, resident=True):
         factors = list(C.draw_given_factors(case, np.random, ml, nl))
     L.pass_count(True, reset=True)
     L.pass_count(False, reset=True)
-    W, H, err = PyNMF(A_ij, factors=factors, params=args).fit()
+    nmf = PyNMF(A_ij, factors=factors, params=args)
+    W, H, err = nmf.fit()
     n_tc, n_generic = L.pass_count(True), L.pass_count(False)
     if case.get('expect_tc'):
         # the large cases exist to pin the tcgen05 kernels: every A-streaming pass must have taken that path
@@ -115,6 +116,7 @@ def fit_worker(rank, world, case, force_generic=False, resident=True):
                 case['name'], n_generic, n_tc)
     out = dict(W=np.asarray(W), H=np.asarray(H), err=float(err), err_dtype=str(np.asarray(err).dtype),
                tc_passes=int(n_tc), generic_passes=int(n_generic),
+               peer_exchange=getattr(getattr(nmf, '_alg', None), '_px', None) is not None,
                geom=[int(v) for v in (args.m, args.n, args.m_loc, args.n_loc, args.W_start, args.W_end,
                                       args.H_start, args.H_end)])
     if case['prune']:
