@@ -38,72 +38,166 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--m', type=int, default=65536)
-    ap.add_argument('--n', type=int, default=65536)
-    ap.add_argument('--k', type=int, default=32)
+    ap.add_argument('--config', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4'],
+                    help='BASELINE.json configuration: cfg2 (default, the headline metric), cfg3 (k=64 on a 2-D grid), cfg4 (HALS/BCD)')
+    ap.add_argument('--m', type=int, default=None)
+    ap.add_argument('--n', type=int, default=None)
+    ap.add_argument('--k', type=int, default=None)
+    ap.add_argument('--no-verify', action='store_true', help='skip the distributed-vs-one-GPU check of the first step')
     ap.add_argument('--norms', default='fro,kl')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-sample', type=int, default=8192, help='side of the square CPU-baseline sample')
+    ap.add_argument('--cpu-sample', type=int, default=32768, help='side of the bounded sample of the in-line cpu_baseline leg')
     ap.add_argument('--force-generic', action='store_true', help='disable the tcgen05 path (A/B runs)')
     ap.add_argument('--no-graph', action='store_true', help='launch every step eagerly instead of replaying a CUDA graph')
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.m_given, a.n_given, a.k_given = a.m is not None, a.n is not None, a.k is not None
+    a.m = a.m if a.m_given else 65536
+    a.n = a.n if a.n_given else 65536
+    a.k = a.k if a.k_given else 32
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port (numpy restatement of the reference's loop) on the host cores
 # ------------------------------------------------------------------------------------------------
-def _cpu_rank_work(q, barrier, shard_rows, side, k, norms, steps, warmup, seed):
-    """One forked 'rank' of a C x 1 row grid: the oracle's update on its own shard, single BLAS thread
-    (the reference forces OMP_NUM_THREADS=1 per MPI rank, main.py:3)."""
+class _RowGridView:
+    """What oracle.nmf_oracle reads of a grid, for ONE forked rank of a C x 1 row grid: per-rank lists have one entry
+    (p = 1) but the 1-D update takes its reducing branches (p_r = C), as a rank of `mpirun -n C` does."""
+
+    def __init__(self, cores):
+        self.p, self.p_r, self.p_c = 1, cores, 1
+        self.world, self.row, self.col = [[0]], [[0]], [[0]]
+        self.coords = [(0, 0)]
+
+
+class _ShmAllreduce:
+    """SUM all-reduce between the forked ranks through shared memory: every rank writes its operand, rank r reduces
+    chunk r over the ranks in rank order, every rank reads the result (reduce-scatter + all-gather, what an MPI
+    all-reduce of this size does).  Stands in for the reference's comm.allreduce (dist_nmf.py:681, :707, :799)."""
+
+    def __init__(self, ctx, cores, max_elems):
+        import ctypes
+        self.cores, self.max_elems = cores, max_elems
+        self.slots = ctx.RawArray(ctypes.c_float, cores * max_elems)
+        self.result = ctx.RawArray(ctypes.c_float, max_elems)
+        self.barrier = ctx.Barrier(cores)
+
+    def bind(self, rank):
+        self.rank = rank
+        self._slots = np.frombuffer(self.slots, dtype=np.float32).reshape(self.cores, self.max_elems)
+        self._result = np.frombuffer(self.result, dtype=np.float32)
+
+    def __call__(self, vals, groups):
+        x = np.ascontiguousarray(vals[0], dtype=np.float32)
+        n = x.size
+        self._slots[self.rank, :n] = x.ravel()
+        self.barrier.wait()
+        per = -(-n // self.cores)
+        lo, hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
+        if hi > lo:
+            acc = self._slots[0, lo:hi].copy()
+            for q in range(1, self.cores):
+                acc += self._slots[q, lo:hi]
+            self._result[lo:hi] = acc
+        self.barrier.wait()
+        out = self._result[:n].reshape(x.shape).astype(vals[0].dtype, copy=True)
+        self.barrier.wait()
+        return [out]
+
+
+def _cpu_rank_work(q, red, rank, cores, shard_rows, n, k, norms, steps, warmup, seed, probe=False):
+    """One forked rank of a C x 1 row grid: the oracle's update on its own row shard, single BLAS thread (the
+    reference forces OMP_NUM_THREADS=1 per MPI rank, main.py:3), all-reducing W^T W / W^T A with the other ranks."""
     try:
         from threadpoolctl import threadpool_limits
         limiter = threadpool_limits(1)
     except Exception:
         limiter = None
     from oracle import nmf_oracle as O
-    rs = np.random.RandomState(seed)
-    A = rs.rand(shard_rows, side).astype(np.float32)
+    red.bind(rank)
+    O.allreduce = red                       # cross-process instead of the in-process virtual-rank reduction
+    rng = np.random.default_rng(seed + rank)
+    A = rng.random((shard_rows, n), dtype=np.float32)
+    rs = np.random.RandomState(7)
+    H0 = rs.rand(k, n).astype(np.float32)   # replicated: identical on every rank
     res = {}
     for norm in norms:
         st = O._State()
-        st.grid, st.k, st.norm, st.method, st.W_update = O.VGrid(1, 1), k, norm, 'mu', True
+        st.grid, st.k, st.norm, st.method, st.W_update = _RowGridView(cores), k, norm, 'mu', True
         st.A, st.dt, st.eps, st.topo = [A], A.dtype, np.finfo(np.float32).eps, '1d'
-        st.W = [rs.rand(shard_rows, k).astype(np.float32)]
-        st.H = [rs.rand(k, side).astype(np.float32)]
+        st.W = [np.random.RandomState(11 + rank).rand(shard_rows, k).astype(np.float32)]
+        st.H = [H0.copy()]
         for i in range(warmup):
             O.update(st, 1)
-        barrier.wait()
+        red.barrier.wait()
         t0 = time.perf_counter()
         for i in range(steps):
             O.update(st, 1)
             if i % 10 == 0:
                 st.H = [np.maximum(h, st.eps) for h in st.H]
                 st.W = [np.maximum(w, st.eps) for w in st.W]
+        red.barrier.wait()
         res[norm] = time.perf_counter() - t0
-        barrier.wait()
+        if probe:                           # tests/test_host_logic.py: the factors this rank ends with
+            res[norm + '_factors'] = (rank, st.W[0], st.H[0])
     q.put(res)
     del limiter
 
 
-def cpu_baseline(args, steps, warmup):
-    """Times oracle.nmf_oracle (kind "port") the way the reference runs on a CPU: C = host cores forked
-    ranks of a C x 1 row grid, one BLAS thread each, every rank updating its own row shard of a bounded
-    square sample concurrently (the k x n all-reduce between ranks is not included: <1 % of the
-    reference's time).  Time = slowest rank; iterations/s are scaled to the full
-    workload by the element ratio (the loop is O(m n k))."""
+def _cpu_sample_side(args, want_full):
+    """Largest square-equivalent sample the host can hold: the KL path of the reference materialises W@H and
+    A/(W@H+eps) (two A-sized temporaries, dist_nmf.py:806) next to A and the generator's scratch."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    m, n = args.m, args.n
+    if not want_full:
+        m, n = min(m, args.cpu_sample), min(n, args.cpu_sample)
+    while m * n * 4 * 5 + (8 << 30) > avail and m > 1024:
+        m //= 2
+        n //= 2
+    return m, n
+
+
+def cpu_probe(m, n, k, norm, steps, cores):
+    """Factors after `steps` iterations of the forked-rank CPU arm (test hook: the shared-memory all-reduce must
+    reproduce the oracle's own virtual-rank result)."""
     import multiprocessing as mp
-    side = min(args.cpu_sample, args.m, args.n)
+    ctx = mp.get_context('fork')
+    q = ctx.Queue()
+    red = _ShmAllreduce(ctx, cores, max(k * n, k * k))
+    shard = m // cores
+    procs = [ctx.Process(target=_cpu_rank_work, args=(q, red, r, cores, shard, n, k, [norm], steps, 0, 1234, True))
+             for r in range(cores)]
+    for p in procs:
+        p.start()
+    out = [q.get()[norm + '_factors'] for _ in procs]
+    for p in procs:
+        p.join()
+    return sorted(out, key=lambda t: t[0])
+
+
+def cpu_baseline(args, steps, warmup, full=False):
+    """Times oracle.nmf_oracle (kind "port") the way the reference runs on a CPU: C = host cores forked ranks of a
+    C x 1 row grid (mpirun -n C), one BLAS thread each, every rank updating its own row shard and all-reducing the
+    k x k / k x n partials with the others through shared memory.  Time = slowest rank.  With `full` the workload
+    is the benchmark's own matrix when the host's memory holds it; otherwise a bounded sample whose iterations/s
+    are scaled by the element ratio (the loop is O(m n k)) -- `sample` says which."""
+    import multiprocessing as mp
+    m, n = _cpu_sample_side(args, full)
     k = args.k
     cores = os.cpu_count() or 1
-    shard = max(1, side // cores)
-    side_rows = shard * cores
-    scale = (side_rows * side) / float(args.m * args.n)
+    shard = max(1, m // cores)
+    m_used = shard * cores
+    scale = (m_used * n) / float(args.m * args.n)
     norms = args.norms.split(',')
     ctx = mp.get_context('fork')
     q = ctx.Queue()
-    barrier = ctx.Barrier(cores)
-    procs = [ctx.Process(target=_cpu_rank_work, args=(q, barrier, shard, side, k, norms, steps, warmup, 1234 + r))
+    red = _ShmAllreduce(ctx, cores, max(k * n, k * k))
+    procs = [ctx.Process(target=_cpu_rank_work, args=(q, red, r, cores, shard, n, k, norms, steps, warmup, 1234))
              for r in range(cores)]
     for p in procs:
         p.start()
@@ -117,30 +211,39 @@ def cpu_baseline(args, steps, warmup):
         out[norm] = steps / dt * scale
         tot_t += dt
     tot_it = steps * len(norms)
+    exact = abs(scale - 1.0) < 1e-9
     return dict(value=tot_it / tot_t * scale, unit='iters/s', cores=int(cores), kind='port',
-                sample='oracle/nmf_oracle.py (numpy %s + OpenBLAS, 1 BLAS thread per rank) as %d forked ranks of a %dx1 '
-                       'grid on a %dx%d k=%d fp32 sample (%d rows per rank), %d timed iterations per norm, slowest rank; '
-                       'iterations/s scaled by the element ratio %.5f to the %dx%d workload'
-                       % (np.__version__, cores, cores, side_rows, side, k, shard, steps, scale, args.m, args.n),
-                by_norm=out)
+                sample=('oracle/nmf_oracle.py (numpy %s + OpenBLAS, 1 BLAS thread per rank) as %d forked ranks of a %dx1 grid '
+                        'on %s %dx%d k=%d fp32 (%d rows per rank), shared-memory all-reduce of W^T W and W^T A between the '
+                        'ranks, %d warm-up + %d timed iterations per norm, slowest rank%s'
+                        % (np.__version__, cores, cores, 'the full workload' if exact else 'a sample', m_used, n, k, shard,
+                           warmup, steps, '' if exact else '; iterations/s scaled by the element ratio %.5f to %dx%d'
+                           % (scale, args.m, args.n))),
+                by_norm=out, measured_s=tot_t, scale=scale)
+
+
+def workload_config(args, world=None):
+    """`config` of both arms (the reference arm runs on this arm's configuration)."""
+    return {'workload': 'synthetic %dx%d fp32 non-negative, KL and FRO MU k=%d (BASELINE.json configs[1]); row grid Nx1, '
+                        'one row shard per GPU' % (args.m, args.n, args.k), 'norms': args.norms}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    warmup = max(1, min(args.warmup, 2))
     t0 = time.perf_counter()
-    cb = cpu_baseline(args, steps, warmup)
+    cb = cpu_baseline(args, max(1, args.steps), max(0, args.warmup), full=True)
     wall = time.perf_counter() - t0
+    steps_total = args.steps * len(args.norms.split(','))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'iters/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': warmup, 'ms_per_step': 1000.0 / cb['value'] if cb['value'] > 0 else None,
+        'steps': args.steps, 'warmup': args.warmup,
+        # measured time per step of what actually ran (equals 1000 / value when the full workload ran)
+        'ms_per_step': 1000.0 * cb['measured_s'] / steps_total,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'synthetic %dx%d fp32 non-negative, KL and FRO MU k=%d (CPU sample, see cpu_baseline.sample)'
-                               % (args.m, args.n, args.k)},
-        'cpu_baseline': cb,
+        'config': workload_config(args),
+        'cpu_baseline': {kk: cb[kk] for kk in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': cb['value'], 'unit': 'iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'by_norm': cb['by_norm'], 'wall_s': wall,
     }
@@ -203,24 +306,53 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # this implementation
 # ------------------------------------------------------------------------------------------------
+# BASELINE.json configs measured by this file (cfg1 / cfg5, the tiny-matrix ones, live in tools/bench_configs.py)
+CONFIGS = {
+    'cfg2': dict(legs=[('fro', 'mu'), ('kl', 'mu')], k=32, scaling='strong', metric=METRIC),
+    'cfg3': dict(legs=[('fro', 'mu')], k=64, scaling='weak',
+                 metric='MU iters/s (FRO, k=64, 65536^2 fp32 per GPU; 262144x131072 on the 4x2 grid of 8 B200)'),
+    'cfg4': dict(legs=[('fro', 'hals'), ('fro', 'bcd')], k=16, scaling='strong',
+                 metric='HALS & BCD iters/s (FRO, k=16, 131072x65536 fp32)'),
+}
+CFG3_GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}
+
+
+def resolve_config(args, world):
+    """(m, n, k, p_r, p_c) of the run.  cfg2 / cfg4: the matrix is fixed, row grid N x 1 (strong scaling).  cfg3: every
+    GPU holds a 65536 x 65536 shard of a (65536 p_r) x (65536 p_c) matrix; 8 GPUs = BASELINE's 262144 x 131072 on 4 x 2."""
+    c = CONFIGS[args.config]
+    if args.config == 'cfg3':
+        p_r, p_c = CFG3_GRIDS[world]
+        side = args.m if args.m_given else 65536
+        return side * p_r, side * p_c, (args.k if args.k_given else c['k']), p_r, p_c
+    if args.config == 'cfg4':
+        m = args.m if args.m_given else 131072
+        n = args.n if args.n_given else 65536
+        return m, n, (args.k if args.k_given else c['k']), world, 1
+    return args.m, args.n, args.k, world, 1
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from pydnmfk_b200 import _lib as L
     from pydnmfk_b200 import device as D
     from pydnmfk_b200.dist_comm import MPI, MPI_comm
-    from pydnmfk_b200.dist_nmf import nmf_algorithms_1D
+    from pydnmfk_b200.dist_nmf import nmf_algorithms_1D, nmf_algorithms_2D
     from pydnmfk_b200.graphs import StepGraphs, graphs_enabled
     from pydnmfk_b200.pyDNMF import PyNMF
-    from pydnmfk_b200.utils import parse, determine_block_params
+    from pydnmfk_b200.utils import parse, determine_block_params, data_operations
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    cfg = CONFIGS[args.config]
+    legs = [l for l in cfg['legs'] if args.config != 'cfg2' or l[0] in args.norms.split(',')]
     # CPU baseline first (forks workers; done before this process creates a CUDA context)
     cb = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 'cfg2':
         cb = cpu_baseline(args, steps=3, warmup=1)
+        cb = {kk: cb[kk] for kk in ('value', 'unit', 'cores', 'kind', 'sample', 'by_norm')}
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -228,71 +360,148 @@ def run_ours(args):
         L.set_force_generic(True)
     comm = MPI.COMM_WORLD          # initialises NCCL from the torchrun environment when world > 1
     assert comm.size == world
-    p_r, p_c = world, 1
+    m, n, k, p_r, p_c = resolve_config(args, world)
     comms = MPI_comm(comm, p_r, p_c)
-    m, n, k = args.m, args.n, args.k
+    two_d = p_r != 1 and p_c != 1
     blk = determine_block_params(rank, (p_r, p_c), (m, n))
-    (r0, _), (r1, _) = blk.determine_block_index_range_asymm()
-    m_loc = r1 - r0 + 1
+    (r0, c0), (r1, c1) = blk.determine_block_index_range_asymm()
+    m_i, n_j = r1 - r0 + 1, c1 - c0 + 1
     eps = float(np.finfo(np.float32).eps)
 
-    def make_params(norm, itr):
+    def make_params(norm, method, itr):
         p = parse()
         p.comm1, p.comm, p.row_comm, p.col_comm = comm, comms, comms.cart_1d_row(), comms.cart_1d_column()
         p.p_r, p.p_c, p.k, p.m, p.n, p.itr, p.init, p.verbose = p_r, p_c, k, m, n, itr, 'rand', False
-        p.norm, p.method, p.prune, p.W_update, p.eps = norm, 'mu', False, True, np.finfo(np.float32).eps
-        p.rank = rank
+        p.norm, p.method, p.prune, p.W_update, p.eps = norm, method, False, True, np.finfo(np.float32).eps
+        p.rank, p.topo = rank, ('2d' if two_d else '1d')
         return p
 
     # synthetic shard, generated on the device (Philox seed 1234 + rank), strictly positive
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
-    A = torch.rand((m_loc, n), generator=g, device=dev, dtype=torch.float32)
-    g.manual_seed(7)
-    W0 = torch.rand((m_loc, k), generator=g, device=dev, dtype=torch.float32)
-    g.manual_seed(7)
-    H0 = torch.rand((k, n), generator=g, device=dev, dtype=torch.float32)
+    A = torch.rand((m_i, n_j), generator=g, device=dev, dtype=torch.float32)
+    dims = data_operations(A, make_params('fro', 'mu', 1)).params
+    w_rows, h_cols = (dims.m_loc, dims.n_loc) if two_d else (m_i, n_j)
+    g.manual_seed(7 + (rank if two_d else 0))
+    W0 = torch.rand((w_rows, k), generator=g, device=dev, dtype=torch.float32)
+    g.manual_seed(7 + (rank if two_d else 0))
+    H0 = torch.rand((k, h_cols), generator=g, device=dev, dtype=torch.float32)
+    if not two_d and world > 1:
+        g.manual_seed(99 + rank)              # row shards of W differ per rank; H is the replicated factor
+        W0 = torch.rand((w_rows, k), generator=g, device=dev, dtype=torch.float32)
     ops = D.default_ops()
+    Alg = nmf_algorithms_2D if two_d else nmf_algorithms_1D
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return float(x)
+
+    # ---- correctness of the distributed step before anything is timed -----------------------------------------
+    # (1) one iteration per leg on the grid vs the same iteration on ONE GPU holding the whole matrix (rank 0
+    #     regenerates every shard from its seed), when the whole matrix fits next to the shard;
+    # (2) replicated factors must be identical on every rank.
+    verify = {}
+    total_bytes = float(m) * n * 4
+    if world > 1 and not args.no_verify:
+        for norm, method in legs:
+            if method == 'bcd':
+                continue                      # BCD scales the factors by a global norm first; covered by tests/
+            W, H = W0.clone(), H0.clone()
+            alg = Alg(A, W, H, params=make_params(norm, method, 1))
+            alg.update()
+            torch.cuda.synchronize()
+            rec = {}
+            if not two_d:
+                ref = H.clone()
+                dist.broadcast(ref, src=0)
+                rec['replica_max_abs_diff'] = allmax(float((H - ref).abs().max().item()))
+                if total_bytes <= 24 * 2 ** 30:
+                    Wall = [torch.empty_like(W0) for _ in range(world)]
+                    dist.all_gather(Wall, W)
+                    W0all = [torch.empty_like(W0) for _ in range(world)]
+                    dist.all_gather(W0all, W0)
+                    if rank == 0:
+                        shards = []
+                        for q in range(world):
+                            gq = torch.Generator(device=dev)
+                            gq.manual_seed(1234 + q)
+                            bq = determine_block_params(q, (p_r, p_c), (m, n)).determine_block_index_range_asymm()
+                            shards.append(torch.rand((bq[1][0] - bq[0][0] + 1, n), generator=gq, device=dev, dtype=torch.float32))
+                        Afull = torch.cat(shards)
+                        del shards
+                        Wf, Hf = torch.cat(W0all), H0.clone()
+                        solo = MPI_comm(type(comm)([rank], None), 1, 1)
+                        ps = make_params(norm, method, 1)
+                        ps.comm1, ps.comm, ps.row_comm, ps.col_comm = solo.comm, solo, solo.cart_1d_row(), solo.cart_1d_column()
+                        ps.p_r, ps.p_c = 1, 1
+                        nmf_algorithms_1D(Afull, Wf, Hf, params=ps).update()
+                        torch.cuda.synchronize()
+                        dW = float((torch.cat(Wall) - Wf).norm() / Wf.norm())
+                        dH = float((H - Hf).norm() / Hf.norm())
+                        rec['vs_one_gpu'] = {'relW': dW, 'relH': dH}
+                        del Afull, Wf, Hf
+                        assert dW < 1e-5 and dH < 1e-5, 'distributed step differs from the 1-GPU step: %r' % rec
+                    del Wall, W0all
+                    torch.cuda.empty_cache()
+                assert rec['replica_max_abs_diff'] <= 1e-6, 'H replicas differ across ranks: %r' % rec
+            verify['%s-%s' % (norm, method)] = rec
+            del alg
+            sync_all()
+
     sampler = ClockSampler(local) if rank == 0 else None
     windows = []
-    by_norm, pass_stats = {}, {}
+    by_leg, pass_stats = {}, {}
     launches = 0
     tot_ms, tot_it = 0.0, 0
     paths = {}
-    for norm in args.norms.split(','):
-        p = make_params(norm, args.steps)
+    for norm, method in legs:
+        leg = '%s-%s' % (norm, method) if args.config != 'cfg2' else norm
+        p = make_params(norm, method, args.steps)
         W, H = W0.clone(), H0.clone()
-        alg = nmf_algorithms_1D(A, W, H, params=p)
+        alg = Alg(A, W, H, params=p)
 
         def clamp():
             ops.clamp_min(H, eps)
             ops.clamp_min(W, eps)
 
-        sg = StepGraphs(alg.update, clamp) if (graphs_enabled(comm, 'mu') and not args.no_graph) else None
+        can_graph = graphs_enabled(comm, 'mu') and not args.no_graph
+        if method == 'bcd':
+            alg.bcd_begin()                        # initWandH once; a step = one iteration of dist_nmf.py:996-1047
+            eager_step, with_clamp = alg.bcd_step, False
+        else:
+            eager_step, with_clamp = alg.update, True
+        sg = StepGraphs(eager_step, clamp if with_clamp else (lambda: None)) if can_graph else None
 
         def step(i):
             # the product's own loop body (PyNMF.fit): CUDA-graph replay of update() [+ clamp every 10th iteration]
             if sg is not None:
-                sg.clamped() if i % 10 == 0 else sg.plain()
+                sg.clamped() if (with_clamp and i % 10 == 0) else sg.plain()
             else:
-                alg.update()
-                if i % 10 == 0:
+                eager_step()
+                if with_clamp and i % 10 == 0:
                     clamp()
 
         L.launch_count(reset=True)
-        alg.update()                       # eager step: sizes the workspace, counts the launches of one step
-        clamp()
+        L.pass_count(True, reset=True)
+        L.pass_count(False, reset=True)
+        eager_step()                       # eager step: sizes the workspace, counts the launches of one step
+        if with_clamp:
+            clamp()
         launches_per_step = L.launch_count()
+        passes_per_step = L.pass_count(True) + L.pass_count(False)
+        paths[leg] = 'tcgen05' if (L.pass_count(True) > 0 and L.pass_count(False) == 0) else (
+            'generic' if L.pass_count(True) == 0 else 'mixed')
         for i in range(args.warmup):
             step(i)
         sync_all()
-        L.launch_count(reset=True)
         ops.timers = {} if sg is None else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_a = time.perf_counter()
@@ -303,29 +512,34 @@ def run_ours(args):
         sync_all()
         t_b = time.perf_counter()
         windows.append((t_a, t_b))
-        ms = e0.elapsed_time(e1)
+        ms = allmax(e0.elapsed_time(e1))
         launches += launches_per_step * args.steps     # same launches per replayed step as in the eager one
-        paths[norm] = 'tcgen05' if L.last_path() == 1 else 'generic'
         if sg is not None:
             # per-kernel CUDA events cannot be placed inside a replayed graph: time the same steps once more, eagerly,
             # with an event pair around every A-streaming pass (not part of `value`)
             ops.timers = {}
             for i in range(min(args.steps, 10)):
-                alg.update()
-                if i % 10 == 0:
+                eager_step()
+                if with_clamp and i % 10 == 0:
                     clamp()
             sync_all()
-        pass_stats[norm] = ops.timer_summary()
+        pass_stats[leg] = ops.timer_summary()
         ops.timers = None
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        by_norm[norm] = {'iters_per_s': args.steps / (ms / 1000.0), 'ms_per_step': ms / args.steps}
+        by_leg[leg] = {'iters_per_s': args.steps / (ms / 1000.0), 'ms_per_step': ms / args.steps,
+                       'a_passes_per_step': int(passes_per_step)}
         tot_ms += ms
         tot_it += args.steps
         assert torch.isfinite(W).all() and torch.isfinite(H).all()
-        del alg, sg, step, clamp      # captured graphs (with their NCCL nodes) must die before the process group does
+        if not two_d and world > 1 and p_c == 1:
+            ref = H.clone()
+            dist.broadcast(ref, src=0)
+            d = allmax(float((H - ref).abs().max().item()))
+            by_leg[leg]['replica_max_abs_diff_after_timed_steps'] = d
+            assert d <= 1e-5, 'H replicas drifted apart across ranks (%g)' % d
+        if getattr(alg, '_px', None) is not None:
+            alg._px.check()
+            by_leg[leg]['h_half_step'] = 'peer-memory exchange (dnmf_xchg_update_h)'
+        del alg, sg, step, clamp, eager_step      # captured graphs (with their NCCL nodes) must die before the process group does
         gc.collect()
         torch.cuda.synchronize()
 
@@ -339,20 +553,20 @@ def run_ours(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
-    pass_bytes = float(m_loc) * n * 4.0
+    pass_bytes = float(m_i) * n_j * 4.0
     per_kernel = {}
     dom = None
-    for norm, st in pass_stats.items():
+    for leg, st in pass_stats.items():
         for opn, (cnt, mean_ms) in st.items():
             gbs = pass_bytes / (mean_ms * 1e-3) / 1e9
-            per_kernel['%s:%s' % (norm, opn)] = {'launches': cnt, 'mean_ms': mean_ms, 'GBps': gbs, 'frac': gbs / peak}
+            per_kernel['%s:%s' % (leg, opn)] = {'launches': cnt, 'mean_ms': mean_ms, 'GBps': gbs, 'frac': gbs / peak}
             if dom is None or cnt * mean_ms > dom[1]:
-                dom = ('%s:%s' % (norm, opn), cnt * mean_ms, gbs)
+                dom = ('%s:%s' % (leg, opn), cnt * mean_ms, gbs)
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (same shard shape only)
     traffic = None
     try:
         cap = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
-        if dom and (cap['m_loc'], cap['n'], cap['k']) == (m_loc, n, k) and dom[0] in cap['kernels']:
+        if dom and (cap['m_loc'], cap['n'], cap['k']) == (m_i, n_j, k) and dom[0] in cap['kernels']:
             traffic = cap['kernels'][dom[0]]['dram_bytes_per_launch']
     except Exception:
         pass
@@ -361,39 +575,35 @@ def run_ours(args):
                 'traffic_source': 'profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)' if traffic else None, 'kernel': dom[0] if dom else None,
                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': pass_bytes, 'per_kernel': per_kernel,
                 'iteration_frac_of_A_streaming_roofline': {
-                    nm: (2.0 * pass_bytes / (v['ms_per_step'] * 1e-3) / 1e9) / peak for nm, v in by_norm.items()}}
+                    nm: (2.0 * pass_bytes / (v['ms_per_step'] * 1e-3) / 1e9) / peak for nm, v in by_leg.items()}}
 
     # ---- end to end through the public API with HOST buffers (PyNMF(A_host).fit()) ----------------
     e2e = None
     if not args.no_e2e:
         try:
-            host = torch.empty((m_loc, n), dtype=torch.float32, pin_memory=True)
+            host = torch.empty((m_i, n_j), dtype=torch.float32, pin_memory=True)
             host.copy_(A)
             torch.cuda.synchronize()
             A_host = host.numpy()
             del A
             torch.cuda.empty_cache()
             e_t, e_it, h2d, d2h = 0.0, 0, 0, 0
-            for norm in args.norms.split(','):
-                p = make_params(norm, args.steps)
+            for norm, method in legs:
+                p = make_params(norm, method, args.steps)
                 np.random.seed(7 + rank)
                 sync_all()
                 t0 = time.perf_counter()
                 Wn, Hn, err = PyNMF(A_host, params=p).fit()
                 torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                if world > 1:
-                    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                    dt = float(t.item())
+                dt = allmax(time.perf_counter() - t0)
                 e_t += dt
                 e_it += args.steps
-                h2d += A_host.nbytes + (m_loc * k + k * n) * 4
+                h2d += A_host.nbytes + (w_rows * k + k * h_cols) * 4
                 d2h += Wn.nbytes + Hn.nbytes + 8
                 assert np.isfinite(float(err))
             e2e = {'value': e_it / e_t, 'unit': 'iters/s', 'h2d_bytes_per_step': h2d * world / e_it,
                    'd2h_bytes_per_step': d2h * world / e_it,
-                   'note': 'PyNMF(A_host, params).fit() with itr=%d per norm: pinned host shard -> HBM copy, rand init on '
+                   'note': 'PyNMF(A_host, params).fit() with itr=%d per leg: pinned host shard -> HBM copy, rand init on '
                            'host, %d iterations, normalise + relative error, factors and error back to host; bytes are '
                            'the whole-fit transfers divided by the iterations' % (args.steps, args.steps)}
         except Exception as ex:  # pinned host memory may be unavailable on a small host
@@ -406,18 +616,20 @@ def run_ours(args):
         clocks = sampler.summary(windows)
 
     if rank == 0:
-        line = {
-            'metric': METRIC, 'value': value, 'unit': 'iters/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': tot_ms / tot_it, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'synthetic %dx%d fp32 non-negative, KL and FRO MU k=%d on %d B200 (grid %dx1, '
-                                   'row shards of %d rows)' % (m, n, k, world, world, m_loc),
+        config = workload_config(args) if args.config == 'cfg2' else {
+            'workload': 'synthetic %dx%d fp32 non-negative, %s, k=%d (BASELINE.json %s)' % (
+                m, n, ' and '.join('%s-%s' % (a.upper(), b.upper()) for a, b in legs), k, args.config)}
+        config.update({'grid': '%dx%d' % (p_r, p_c), 'shard': '%dx%d per GPU' % (m_i, n_j),
                        'l2': 'inputs larger than L2 (one A pass streams %.1f GiB per GPU)' % (pass_bytes / 2 ** 30),
-                       'norms': args.norms, 'math_mode': 'fp32-accurate', 'paths': paths,
-                       'launch': 'cuda-graph replay of update()+clamp (as PyNMF.fit does)' if not args.no_graph else 'eager',
-                       'roofline_timing': 'CUDA events around each A-streaming pass, eager replica of the timed steps' if not args.no_graph else 'CUDA events around each A-streaming pass inside the timed steps'},
-            'by_norm': by_norm, 'roofline': roofline, 'cpu_baseline': cb, 'e2e': e2e, 'gpu_launches': int(launches),
-            'clocks': clocks,
+                       'math_mode': 'fp32-accurate', 'paths': paths,
+                       'launch': 'cuda-graph replay of the step (as PyNMF.fit does)' if not args.no_graph else 'eager',
+                       'roofline_timing': 'CUDA events around each A-streaming pass, eager replica of the timed steps' if not args.no_graph else 'CUDA events around each A-streaming pass inside the timed steps'})
+        line = {
+            'metric': cfg['metric'], 'value': value, 'unit': 'iters/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': tot_ms / tot_it, 'higher_is_better': True, 'scaling': cfg['scaling'],
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+            ('by_norm' if args.config == 'cfg2' else 'by_leg'): by_leg, 'roofline': roofline, 'cpu_baseline': cb, 'e2e': e2e,
+            'gpu_launches': int(launches), 'clocks': clocks, 'verify': verify or None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

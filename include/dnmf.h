@@ -57,6 +57,7 @@ extern "C" {
 #define DNMF_OP_RESIDUAL 5
 #define DNMF_OP_SUMS 6
 #define DNMF_OP_NNZ 7
+#define DNMF_OP_AH_RESIDUAL 8
 
 const char* dnmf_version(void);
 const char* dnmf_last_error(void);
@@ -74,6 +75,9 @@ int dnmf_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int dnmf_set_force_generic(int on);
 /* smallest shard (m*n elements) routed to the tcgen05 path; default 2^20, tests lower it */
 int dnmf_set_tc_min_elems(int64_t elems);
+/* 1: dnmf_residual_sqnorm uses the tcgen05 pipeline (fp32, k <= 32) instead of the CUDA-core kernel; default 0
+ * (or the DNMF_TC_RESIDUAL environment variable) */
+int dnmf_set_tc_residual(int on);
 /* debug: timing-ablation bits of the tcgen05 kernels (tools/prof_tc.py); non-zero values give WRONG results */
 int dnmf_set_tc_debug(int flags);
 /* debug/profiling: device buffer of [n_sm][16] uint64 cycle counters filled by the tcgen05 kernels (NULL = off) */
@@ -269,6 +273,32 @@ int dnmf_mu_fit_resident_cluster_size(int64_t m, int64_t n, int64_t k, int kl, i
 int dnmf_mu_fit_resident(const void* const* A_ptrs, int64_t lda, void* const* W_ptrs, void* const* H_ptrs, int64_t batch,
                          int64_t m, int64_t n, int64_t k, int kl, int w_update, int64_t it_begin, int64_t it_end,
                          double eps, int dtype, void* stream);
+
+/* V = A H^T and out[0] = ||A - W H||_F^2, out[1] = ||A||_F^2 in ONE pass over A (fp32, k <= 32: tcgen05 kernel that
+ * recomputes each W H tile on the tensor cores like the KL path; otherwise the two separate passes): the BCD iteration's
+ * dist_nmf.py:1023 (A H^T) and :1024 (objective), which the reference runs as two passes plus an m x n temporary. */
+int dnmf_ah_residual(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh, void* V,
+                     int64_t ldv, int64_t m, int64_t n, int64_t k, double* out, int dtype, void* ws, int64_t ws_bytes,
+                     void* stream);
+
+/* ---- FRO-BCD with its scalars on the device (dist_nmf.py:996-1047): the same arithmetic as dnmf_bcd_pg_w / _h with the
+ * Lipschitz bound read from device memory, and the iteration's control state (Lipschitz bounds, objective, momentum
+ * weights, accept / restore decision) kept in a 16-double device vector:
+ *   state[0] L_W  [1] L_W old  [2] L_H  [3] L_H old  [4] obj_old  [5] t_old  [6] accept  [7] ww  [8] wh  [9] obj
+ *   [10] rw  [11] restores so far
+ * dnmf_bcd_state phase 0: in[0] = ||A||^2 (init, :951-969); 1: in[0] = ||H H^T||_F^2 (:1000-1001); 2: in[0] =
+ * ||W^T W||_F^2 (:1016-1017); 3: in[0] = ||A - W H||_F^2 -> obj, t, ww, wh, accept (:1024-1047).
+ * dnmf_bcd_advance (which 0 = W with ww, 1 = H with wh): accept -> Xm = X + w (X - X_old), X_old = X; restore -> Xm = X_old.
+ * dnmf_bcd_keep: accept -> kept = cur; restore -> cur = kept  (H H^T and A H^T of the last accepted H, instead of the
+ * reference's recomputation :1034-1035, which costs another pass over A). */
+int dnmf_bcd_pg_w_dev(void* W, int64_t ldw, const void* Wm, int64_t ldwm, const void* V, int64_t ldv, const void* G,
+                      int64_t m, int64_t k, const double* L_dev, int dtype, void* stream);
+int dnmf_bcd_pg_h_dev(void* H, int64_t ldh, const void* Hm, int64_t ldhm, const void* Y, int64_t y_stride_k,
+                      int64_t y_stride_c, const void* G, int64_t k, int64_t n, const double* L_dev, int dtype, void* stream);
+int dnmf_bcd_state(int phase, double* state, const double* in, void* stream);
+int dnmf_bcd_advance(const void* X, void* Xm, void* X_old, int64_t count, const double* state, int which, int dtype,
+                     void* stream);
+int dnmf_bcd_keep(void* cur, void* kept, int64_t count, const double* state, int dtype, void* stream);
 
 /* ---- communicators: dist_comm.py:16-56 (MPI_comm: world + row / column sub-communicators) as NCCL communicators
  * owned by this library, one process per GPU.  The 128-byte id is created on one rank (dnmf_comm_unique_id) and

@@ -112,6 +112,12 @@ def _grid_cases():
         c = _case('%sk%d_%dx%d_%s_mu_i%d' % (tag, k, g[0], g[1], norm, itr), m, n, k, g, norm, 'mu', itr, reseed=7)
         c['expect_tc'] = True
         cs.append(c)
+    # BCD / HALS on the tensor path (cfg4 in miniature: k = 16): the BCD iteration's fused A H^T + residual pass
+    for g in ((1, 1), (2, 1), (2, 2)):
+        for method in ('bcd', 'hals'):
+            c = _case('u2048k16_%dx%d_fro_%s_i10' % (g + (method,)), 2048, 2048, 16, g, 'fro', method, 10, reseed=7)
+            c['expect_tc'] = True
+            cs.append(c)
     # prune path: exact-zero rows/cols, fp32 in -> float64 out (utils.py:195,198)
     for g in ((1, 1), (2, 1), (1, 2), (2, 2)):
         for norm in ('fro', 'kl'):

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('DNMF_LIB_PATH') or os.path.join(_HERE, 'libdnmf.so') 
 
 F32, F64, I64 = 0, 1, 2
 MATH_ACCURATE, MATH_TF32 = 0, 1
-OP_AH, OP_WTA, OP_KL_UHT, OP_KL_WTU, OP_GRAM, OP_RESIDUAL, OP_SUMS, OP_NNZ = range(8)
+OP_AH, OP_WTA, OP_KL_UHT, OP_KL_WTU, OP_GRAM, OP_RESIDUAL, OP_SUMS, OP_NNZ, OP_AH_RESIDUAL = range(9)
 MAX_K = 64
 
 i64, i32, dbl, vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
@@ -29,6 +29,7 @@ SIGNATURES = {
     'dnmf_set_tc_min_elems': (i32, [i64]),
     'dnmf_set_tc_profile': (i32, [vp]),
     'dnmf_set_tc_debug': (i32, [i32]),
+    'dnmf_set_tc_residual': (i32, [i32]),
     'dnmf_workspace_bytes': (i64, [i32, i64, i64, i64, i32]),
     'dnmf_ah': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, i32, vp, i64, vp]),
     'dnmf_wta': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, i32, i32, vp, i64, vp]),
@@ -45,12 +46,18 @@ SIGNATURES = {
     'dnmf_sqnorm': (i32, [vp, i64, i64, i64, vp, i32, vp, i64, vp]),
     'dnmf_normalize': (i32, [vp, i64, i64, vp, i64, i64, i64, vp, dbl, i32, vp]),
     'dnmf_residual_sqnorm': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp, i32, vp, i64, vp]),
+    'dnmf_ah_residual': (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, i64, vp, i32, vp, i64, vp]),
     'dnmf_column_err': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp, vp, i32, vp]),
     'dnmf_hals_w_col': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, dbl, vp, i32, vp, i64, vp]),
     'dnmf_div_col': (i32, [vp, i64, i64, i64, vp, i32, vp]),
     'dnmf_hals_h': (i32, [vp, i64, vp, i64, i64, vp, i64, i64, dbl, i32, vp]),
     'dnmf_bcd_pg_w': (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, dbl, i32, vp]),
     'dnmf_bcd_pg_h': (i32, [vp, i64, vp, i64, vp, i64, i64, vp, i64, i64, dbl, i32, vp]),
+    'dnmf_bcd_pg_w_dev': (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, vp, i32, vp]),
+    'dnmf_bcd_pg_h_dev': (i32, [vp, i64, vp, i64, vp, i64, i64, vp, i64, i64, vp, i32, vp]),
+    'dnmf_bcd_state': (i32, [i32, vp, vp, vp]),
+    'dnmf_bcd_advance': (i32, [vp, vp, vp, i64, vp, i32, i32, vp]),
+    'dnmf_bcd_keep': (i32, [vp, vp, i64, vp, i32, vp]),
     'dnmf_div_cols': (i32, [vp, i64, i64, i64, vp, i32, vp]),
     'dnmf_axpby': (i32, [vp, vp, vp, dbl, dbl, i64, i32, vp]),
     'dnmf_nnz_counts': (i32, [vp, i64, i64, i64, vp, vp, i32, vp]),
@@ -100,7 +107,7 @@ SIGNATURES = {
 }
 
 _NO_STATUS = {'dnmf_xchg_bytes', 'dnmf_pass_count', 'dnmf_version', 'dnmf_last_error', 'dnmf_last_path', 'dnmf_launch_count', 'dnmf_workspace_bytes',
-              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile', 'dnmf_set_tc_debug', 'dnmf_colsum_workspace_bytes',
+              'dnmf_set_force_generic', 'dnmf_set_tc_min_elems', 'dnmf_set_tc_profile', 'dnmf_set_tc_debug', 'dnmf_set_tc_residual', 'dnmf_colsum_workspace_bytes',
               'dnmf_matvec_workspace_bytes', 'dnmf_mu_fit_resident_smem_bytes', 'dnmf_mu_fit_resident_cluster_size'}
 
 

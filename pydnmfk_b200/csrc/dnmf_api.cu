@@ -59,6 +59,17 @@ int64_t dnmf_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype)
       }
       break;
     }
+    case DNMF_OP_AH_RESIDUAL: {
+      // fused tcgen05 pass, or (fallback) the A H^T pass followed by the residual pass in the same workspace
+      const int64_t a = dnmf_workspace_bytes(DNMF_OP_AH, m, n, k, dtype);
+      const int64_t r = dnmf_workspace_bytes(DNMF_OP_RESIDUAL, m, n, k, dtype);
+      bytes = a > r ? a : r;
+      if (dtype == DNMF_F32 && k <= 32) {
+        const int64_t t = tc_ah_residual_workspace_bytes(m, n);
+        if (t > bytes) bytes = t;
+      }
+      break;
+    }
     case DNMF_OP_SUMS: {
       // max over: colsum(m x k), rowsum(k x n), sqnorm(m x n | m x k | k x n), hals_w_col(m)
       int64_t d = 0, v;
@@ -177,28 +188,39 @@ int dnmf_mu_update_w(void* W, int64_t ldw, const void* V, int64_t ldv, const voi
   DNMF_CHECK_ARG(W && V && G, "null pointer");
   if (m == 0 || k == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_T(dtype, return row_update_dispatch<T>(0, (T*)W, ldw, (const T*)W, ldw, (const T*)V, ldv, (const T*)G, m, (int)k, (T)eps, st));
+  DISPATCH_T(dtype, return row_update_dispatch<T>(0, (T*)W, ldw, (const T*)W, ldw, (const T*)V, ldv, (const T*)G, m, (int)k, (T)eps, nullptr, st));
+  return 0;
+}
+
+static int bcd_pg_w(void* W, int64_t ldw, const void* Wm, int64_t ldwm, const void* V, int64_t ldv, const void* G,
+                    int64_t m, int64_t k, double L, const double* L_dev, int dtype, void* stream) {
+  if (int rc = check_common(m, 0, k, dtype)) return rc;
+  DNMF_CHECK_ARG(W && Wm && V && G, "null pointer");
+  if (m == 0 || k == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, return row_update_dispatch<T>(1, (T*)W, ldw, (const T*)Wm, ldwm, (const T*)V, ldv, (const T*)G, m, (int)k, (T)L, L_dev, st));
   return 0;
 }
 
 int dnmf_bcd_pg_w(void* W, int64_t ldw, const void* Wm, int64_t ldwm, const void* V, int64_t ldv, const void* G,
                   int64_t m, int64_t k, double L, int dtype, void* stream) {
-  if (int rc = check_common(m, 0, k, dtype)) return rc;
-  DNMF_CHECK_ARG(W && Wm && V && G, "null pointer");
-  if (m == 0 || k == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_T(dtype, return row_update_dispatch<T>(1, (T*)W, ldw, (const T*)Wm, ldwm, (const T*)V, ldv, (const T*)G, m, (int)k, (T)L, st));
-  return 0;
+  return bcd_pg_w(W, ldw, Wm, ldwm, V, ldv, G, m, k, L, nullptr, dtype, stream);
+}
+
+int dnmf_bcd_pg_w_dev(void* W, int64_t ldw, const void* Wm, int64_t ldwm, const void* V, int64_t ldv, const void* G,
+                      int64_t m, int64_t k, const double* L_dev, int dtype, void* stream) {
+  DNMF_CHECK_ARG(L_dev, "null Lipschitz pointer");
+  return bcd_pg_w(W, ldw, Wm, ldwm, V, ldv, G, m, k, 1.0, L_dev, dtype, stream);
 }
 
 static int col_update(int mode, void* H, int64_t ldh, const void* X, int64_t ldx, const void* Y, int64_t ysk,
                       int64_t ysc, const void* G, int64_t k, int64_t n, double p0, int clamp, int dtype,
-                      void* stream) {
+                      void* stream, const double* p0_dev = nullptr) {
   if (int rc = check_common(0, n, k, dtype)) return rc;
   DNMF_CHECK_ARG(H && X && Y && G, "null pointer");
   if (n == 0 || k == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_T(dtype, return col_update_dispatch<T>(mode, (T*)H, ldh, (const T*)X, ldx, (const T*)Y, ysk, ysc, (const T*)G, (int)k, n, (T)p0, clamp, st));
+  DISPATCH_T(dtype, return col_update_dispatch<T>(mode, (T*)H, ldh, (const T*)X, ldx, (const T*)Y, ysk, ysc, (const T*)G, (int)k, n, (T)p0, clamp, p0_dev, st));
   return 0;
 }
 
@@ -210,6 +232,12 @@ int dnmf_mu_update_h(void* H, int64_t ldh, const void* Y, int64_t y_stride_k, in
 int dnmf_bcd_pg_h(void* H, int64_t ldh, const void* Hm, int64_t ldhm, const void* Y, int64_t y_stride_k,
                   int64_t y_stride_c, const void* G, int64_t k, int64_t n, double L, int dtype, void* stream) {
   return col_update(1, H, ldh, Hm, ldhm, Y, y_stride_k, y_stride_c, G, k, n, L, 0, dtype, stream);
+}
+
+int dnmf_bcd_pg_h_dev(void* H, int64_t ldh, const void* Hm, int64_t ldhm, const void* Y, int64_t y_stride_k,
+                      int64_t y_stride_c, const void* G, int64_t k, int64_t n, const double* L_dev, int dtype, void* stream) {
+  DNMF_CHECK_ARG(L_dev, "null Lipschitz pointer");
+  return col_update(1, H, ldh, Hm, ldhm, Y, y_stride_k, y_stride_c, G, k, n, 1.0, 0, dtype, stream, L_dev);
 }
 
 int dnmf_hals_h(void* H, int64_t ldh, const void* Y, int64_t y_stride_k, int64_t y_stride_c, const void* G,
@@ -377,6 +405,29 @@ int dnmf_residual_sqnorm(const void* A, int64_t lda, const void* W, int64_t ldw,
   sum_pairs_kernel<<<1, 256, 0, st>>>((const double*)ws, nb, out);
   DNMF_LAUNCH_CHECK("sum_pairs_kernel");
   return 0;
+}
+
+int dnmf_ah_residual(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh, void* V,
+                     int64_t ldv, int64_t m, int64_t n, int64_t k, double* out, int dtype, void* ws, int64_t ws_bytes,
+                     void* stream) {
+  if (int rc = check_common(m, n, k, dtype)) return rc;
+  DNMF_CHECK_ARG(A && W && H && V && out, "null pointer");
+  DNMF_CHECK_ARG(lda >= n && ldh >= n && ldw >= k && ldv >= k, "leading dimension too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m > 0 && n > 0 && k >= 1 && k <= 32 && tc_eligible(DNMF_OP_KL_UHT, A, lda, m, n, k, dtype)) {
+    double* pairs = nullptr;
+    int64_t n_pairs = 0;
+    tls().last_path = 1;
+    tls().tc_passes++;
+    if (int rc = tc_ah_residual_run((const float*)A, lda, (const float*)W, ldw, (const float*)H, ldh, (float*)V, ldv, m, n,
+                                    (int)k, ws, ws_bytes, &pairs, &n_pairs, st))
+      return rc;
+    sum_pairs_kernel<<<1, 256, 0, st>>>(pairs, n_pairs, out);
+    DNMF_LAUNCH_CHECK("sum_pairs_kernel");
+    return 0;
+  }
+  if (int rc = dnmf_ah(A, lda, H, ldh, V, ldv, m, n, k, dtype, DNMF_MATH_ACCURATE, ws, ws_bytes, stream)) return rc;
+  return dnmf_residual_sqnorm(A, lda, W, ldw, H, ldh, m, n, k, out, dtype, ws, ws_bytes, stream);
 }
 
 int dnmf_column_err(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh, int64_t m,

@@ -88,6 +88,11 @@ int dnmf_set_tc_profile(void* buf) {
   return 0;
 }
 
+int dnmf_set_tc_residual(int on) {
+  tc_set_residual(on);
+  return 0;
+}
+
 int dnmf_set_tc_debug(int flags) {
   tc_set_debug(flags);
   return 0;

@@ -12,8 +12,11 @@
 // Both GEMMs use the 3-term tf32 split (see dnmf_tc.cu) so the result is fp32-accurate; U and U_lo go to the TMEM
 // operand ring like A and A_lo do on the FRO path.  The MMA warp issues GEMM1 two tiles ahead of GEMM2.
 //
-// MODE 2 (residual, opt-in via DNMF_TC_RESIDUAL=1, see tc_residual_run): the same GEMM1 and tile traffic, but the
-// splitters accumulate sum (A - S)^2 and sum A^2 instead of forming U; GEMM2, its B producer and the drain warps idle.
+// MODE 2 (residual only, tc_residual_run): the same GEMM1 and tile traffic, but the splitters accumulate sum (A - S)^2 and
+// sum A^2 instead of forming U; GEMM2, its B producer and the drain warps idle.
+// MODE 3 (A H^T AND residual in one pass, tc_ah_residual_run; the BCD iteration's second pass, dist_nmf.py:1023-1024):
+// rows of A like MODE 0, U = A itself (so GEMM2 yields V = A H^T exactly as the FRO kernel does), and the splitters
+// accumulate the residual terms on the side.
 //
 // Warp roles (512 threads, one persistent CTA per SM): w0 A-TMA | w1 MMA issuer | w2-5, w11-14 splitter groups |
 // w6-9 drain | w10 Bcat-TMA (lane 0) + Fr-TMA (lane 1) | w15 GEMM1 issuer.
@@ -73,7 +76,8 @@ __global__ void __launch_bounds__(KL_THREADS, 1)
 tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmF, const float* __restrict__ Fx, int64_t ldfx, int64_t fr_rows_pad,
              float* __restrict__ P, int64_t split_stride, int64_t x_len, int x_blocks, int kt_total, int kt_per_split,
-             int num_units, int k_real, float eps, int dbg, unsigned long long* __restrict__ prof) {
+             int num_units, int k_real, float eps, int dbg, double* __restrict__ pairs_out,
+             unsigned long long* __restrict__ prof) {
   // dbg (dnmf_set_tc_debug, timing ablations only -- results become wrong): 1 skip the division, 2 skip the S load,
   // 4 skip the GEMM1 MMAs, 8 skip the GEMM2 low-order MMAs, 16 skip all GEMM2 MMAs, 32 skip the U split, 64 skip the
   // shared-memory read of the A tile, 0x10000 skip the Bcat TMA loads, 0x20000 skip the FrCat TMA loads
@@ -355,7 +359,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld_wait();
 #define KL_S_OF(j) (__uint_as_float(s0[j]) + __uint_as_float(s1[j]))
 #endif
-          if (MODE == 2) {
+          if (MODE == 2 || MODE == 3) {
             // residual: this row's 32 elements of (A - W H)^2 and A^2, fp32 within the tile, float64 across tiles
             float t_res = 0.f, t_a = 0.f;
 #pragma unroll
@@ -367,6 +371,8 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             res_sum += (double)t_res;
             a_sum += (double)t_a;
+          }
+          if (MODE == 2) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -376,7 +382,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             continue;
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; MODE != 3 && j < 32; ++j) {
             const float den = KL_S_OF(j) + eps;
             const float a = __uint_as_float(u[j]);
             // den >= eps > 0 and far from overflow: one MUFU.RCP (1 ulp) and one multiply, no range handling.  The
@@ -413,9 +419,9 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(bar(iTF + ts));
       }
     }
-    if (MODE == 2) {
+    if (MODE == 2 || MODE == 3) {
       // one (residual, norm) pair per splitter thread; summed in a fixed order by the caller
-      double* pairs = reinterpret_cast<double*>(P) + ((int64_t)blockIdx.x * 256 + (group * 4 + q) * 32 + lane) * 2;
+      double* pairs = pairs_out + ((int64_t)blockIdx.x * 256 + (group * 4 + q) * 32 + lane) * 2;
       pairs[0] = res_sum;
       pairs[1] = a_sum;
     }
@@ -605,7 +611,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
     }
     kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmB, tmF, Fx, ldfx, kp.r_pad, P, split_stride, x_len,
                                                           pl.x_blocks, pl.kt_total, pl.kt_per_split, pl.num_units,
-                                                          k_real, eps, tc_dbg_flags(), tc_prof_ptr());
+                                                          k_real, eps, tc_dbg_flags(), nullptr, tc_prof_ptr());
     DNMF_LAUNCH_CHECK("tc_kl_kernel");
     return 0;
   };
@@ -621,15 +627,71 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   return 0;
 }
 
+// ---- V = A H^T together with ||A - W H||^2 and ||A||^2 in ONE pass over A (MODE 3) -------------------------------------
+// ws = [Bcat | FrCat | partials | pairs (grid x 256 x 2 float64)]
+int64_t tc_ah_residual_workspace_bytes(int64_t m, int64_t n) {
+  const KlPlan p = kl_plan(0, m, n);
+  return p.base.bcat_bytes + p.frcat_bytes + p.base.partial_bytes + round_up((int64_t)p.base.grid * 256 * 2 * (int64_t)sizeof(double), 1024);
+}
+
+int tc_ah_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* V,
+                       int64_t ldv, int64_t m, int64_t n, int k, void* ws, int64_t ws_bytes, double** out_pairs,
+                       int64_t* n_pairs, cudaStream_t st) {
+  if (k < 1 || k > KK) return fail(DNMF_E_UNSUPPORTED, "tcgen05 A H^T + residual: k must be in [1, %d]", KK);
+  const KlPlan kp = kl_plan(0, m, n);
+  const TcPlan& pl = kp.base;
+  const int64_t need = tc_ah_residual_workspace_bytes(m, n);
+  if (ws == nullptr || ws_bytes < need)
+    return fail(DNMF_E_WORKSPACE, "tcgen05 A H^T + residual needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  if (((uintptr_t)ws % 256) != 0) return fail(DNMF_E_ARG, "workspace must be 256-byte aligned");
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  float* Bcat = reinterpret_cast<float*>(wsb);
+  float* FrCat = reinterpret_cast<float*>(wsb + pl.bcat_bytes);
+  float* P = reinterpret_cast<float*>(wsb + pl.bcat_bytes + kp.frcat_bytes);
+  double* pairs = reinterpret_cast<double*>(wsb + pl.bcat_bytes + kp.frcat_bytes + pl.partial_bytes);
+  if (k != KK) {
+    cudaError_t e = cudaMemsetAsync(Bcat, 0, (size_t)pl.bcat_bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "Bcat memset");
+  }
+  tc_launch_split_h(H, ldh, Bcat, pl.ldb, k, KK, n, st);
+  kl_split_fr_kernel<true><<<(unsigned)ceil_div(kp.r_pad, 64), 256, 0, st>>>(H, ldh, FrCat, n, kp.r_pad, k);
+  DNMF_LAUNCH_CHECK("kl_split_fr_kernel<T>");
+  alignas(64) CUtensorMap tmA, tmB, tmF;
+  int rc = tc_make_map(&tmA, A, m, n, lda, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = tc_make_map(&tmB, Bcat, 2 * KK, n, pl.ldb, TC_BK, 2 * KK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  auto kern = tc_kl_kernel<3>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, KlCfg::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "tc_kl_kernel<3> smem attribute");
+    attr_set = true;
+  }
+  const int64_t split_stride = m * KK;
+  kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmB, tmF, W, ldw, kp.r_pad, P, split_stride, m, pl.x_blocks,
+                                                        pl.kt_total, pl.kt_per_split, pl.num_units, k, 0.f, tc_dbg_flags(),
+                                                        pairs, tc_prof_ptr());
+  DNMF_LAUNCH_CHECK("tc_kl_kernel<3>");
+  reduce_partials_kernel<float><<<(unsigned)ceil_div(m * k, 256), 256, 0, st>>>(P, split_stride, pl.splits, m, k, V, ldv, 1, KK);
+  DNMF_LAUNCH_CHECK("reduce_partials_kernel");
+  *out_pairs = pairs;
+  *n_pairs = (int64_t)pl.grid * 256;
+  return 0;
+}
+
 // ---- ||A - W H||^2 and ||A||^2 through the same pipeline (MODE 2) ---------------------------------------------------
 // Opt-in (DNMF_TC_RESIDUAL=1): written at the end of round 1 and NOT yet run on hardware; the default stays the
 // CUDA-core residual kernel.  ws = [FrCat | pairs (grid x 256 x 2 float64)]; out_pairs receives the per-thread pairs,
 // *n_pairs their count (the caller sums them in a fixed order).
+namespace { int g_tc_residual = -1; }
 bool tc_residual_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("DNMF_TC_RESIDUAL"); on = (e && atoi(e) != 0) ? 1 : 0; }
-  return on == 1;
+  if (g_tc_residual < 0) { const char* e = getenv("DNMF_TC_RESIDUAL"); g_tc_residual = (e && atoi(e) != 0) ? 1 : 0; }
+  return g_tc_residual == 1;
 }
+void tc_set_residual(int on) { g_tc_residual = on ? 1 : 0; }
 
 int64_t tc_residual_workspace_bytes(int64_t m, int64_t n) {
   const KlPlan p = kl_plan(0, m, n);
@@ -663,9 +725,9 @@ int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, co
     attr_set = true;
   }
   // (the GEMM2 operand map is unused in this mode: tmF stands in for it)
-  kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmF, tmF, W, ldw, kp.r_pad, reinterpret_cast<float*>(pairs), 0, m,
+  kern<<<pl.grid, KL_THREADS, KlCfg::SMEM_BYTES, st>>>(tmA, tmF, tmF, W, ldw, kp.r_pad, nullptr, 0, m,
                                                         pl.x_blocks, pl.kt_total, pl.kt_per_split, pl.num_units, k, 0.f,
-                                                        0, tc_prof_ptr());
+                                                        0, pairs, tc_prof_ptr());
   DNMF_LAUNCH_CHECK("tc_kl_kernel<2>");
   *out_pairs = pairs;
   *n_pairs = (int64_t)pl.grid * 256;

@@ -83,7 +83,10 @@ struct RowUpdCfg {
 template <typename T, int KP, int MODE>
 __global__ void __launch_bounds__(kRowUpdThreads)
 row_update_kernel(T* __restrict__ W, int64_t ldw, const T* __restrict__ X, int64_t ldx,
-                  const T* __restrict__ V, int64_t ldv, const T* __restrict__ G, int64_t m, int k, T p0) {
+                  const T* __restrict__ V, int64_t ldv, const T* __restrict__ G, int64_t m, int k, T p0,
+                  const double* __restrict__ p0_dev) {
+  // p0_dev != nullptr: the scalar (BCD's Lipschitz bound) lives on the device (no host round trip, graph-capturable)
+  if (p0_dev != nullptr) p0 = (T)p0_dev[0];
   constexpr int NT = kRowUpdThreads, RB = RowUpdCfg<T, KP>::RB;
   __shared__ T Gs[KP][KP + 1];
   __shared__ T Xs[RB][KP + 1];
@@ -131,7 +134,8 @@ template <typename T, int KP, int MODE>
 __global__ void __launch_bounds__(kColUpdThreads)
 col_update_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ X, int64_t ldx,
                   const T* __restrict__ Y, int64_t ysk, int64_t ysc, const T* __restrict__ G,
-                  int k, int64_t n, T p0, int clamp) {
+                  int k, int64_t n, T p0, int clamp, const double* __restrict__ p0_dev) {
+  if (p0_dev != nullptr) p0 = (T)p0_dev[0];
   __shared__ T Gs[KP * KP];
   const int t = threadIdx.x;
   for (int idx = t; idx < KP * KP; idx += kColUpdThreads) {

@@ -23,9 +23,16 @@ int tc_kl_wtu(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
               int64_t ldy, int64_t m, int64_t n, int k, float eps, int transposed_out, int math_mode, void* ws,
               int64_t ws_bytes, cudaStream_t st);
 
+// V = A H^T plus ||A - W H||^2, ||A||^2 in one pass (fp32, k <= 32): per-thread float64 pairs like tc_residual_run
+int64_t tc_ah_residual_workspace_bytes(int64_t m, int64_t n);
+int tc_ah_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* V,
+                       int64_t ldv, int64_t m, int64_t n, int k, void* ws, int64_t ws_bytes, double** out_pairs,
+                       int64_t* n_pairs, cudaStream_t st);
+
 // ||A - W H||^2, ||A||^2 on the tcgen05 pipeline (opt-in, DNMF_TC_RESIDUAL=1; fp32, k <= 32): per-thread float64 pairs in
 // the workspace, to be summed by the caller in a fixed order.
 bool tc_residual_enabled();
+void tc_set_residual(int on);
 int64_t tc_residual_workspace_bytes(int64_t m, int64_t n);
 int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, int64_t m,
                     int64_t n, int k, void* ws, int64_t ws_bytes, double** out_pairs, int64_t* n_pairs, cudaStream_t st);

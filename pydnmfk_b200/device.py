@@ -253,6 +253,20 @@ class DeviceOps:
                out.data_ptr(), dt, ws, wsb, self._stream())
         return out
 
+    def ah_residual(self, A, W, H):
+        """(A @ H.T, [||A - W H||_F^2, ||A||_F^2]) in one pass over A (dist_nmf.py:1023-1024)."""
+        m, n = A.shape
+        k = W.shape[1]
+        dt = _DT[A.dtype]
+        V = self.empty((m, k), A.dtype)
+        out = self.empty((2,), torch.float64)
+        ws, wsb = self._ws_for(L.OP_AH_RESIDUAL, m, n, k, dt)
+        ev = self._t0('ah_res')
+        L.call('dnmf_ah_residual', A.data_ptr(), _ld(A), W.data_ptr(), _ld(W), H.data_ptr(), _ld(H), V.data_ptr(), _ld(V),
+               m, n, k, out.data_ptr(), dt, ws, wsb, self._stream())
+        self._t1(ev)
+        return V, out
+
     def column_err(self, A, W, H):
         m, n = A.shape
         k = W.shape[1]
@@ -290,6 +304,32 @@ class DeviceOps:
         sk, sc = self._ystrides(Y, y_transposed)
         L.call('dnmf_bcd_pg_h', H.data_ptr(), _ld(H), Hm.data_ptr(), _ld(Hm), Y.data_ptr(), sk, sc, G.data_ptr(),
                k, n, float(Lip), _DT[H.dtype], self._stream())
+
+    # BCD with device-resident scalars (dnmf_bcd.cu): `state` is a 16-element float64 device vector
+    def bcd_pg_w_dev(self, W, Wm, V, G, state, idx):
+        m, k = W.shape
+        L.call('dnmf_bcd_pg_w_dev', W.data_ptr(), _ld(W), Wm.data_ptr(), _ld(Wm), V.data_ptr(), _ld(V), G.data_ptr(),
+               m, k, state.data_ptr() + 8 * idx, _DT[W.dtype], self._stream())
+
+    def bcd_pg_h_dev(self, H, Hm, Y, G, state, idx, y_transposed=False):
+        k, n = H.shape
+        sk, sc = self._ystrides(Y, y_transposed)
+        L.call('dnmf_bcd_pg_h_dev', H.data_ptr(), _ld(H), Hm.data_ptr(), _ld(Hm), Y.data_ptr(), sk, sc, G.data_ptr(),
+               k, n, state.data_ptr() + 8 * idx, _DT[H.dtype], self._stream())
+
+    def bcd_state(self, phase, state, scalar_in):
+        assert state.dtype == torch.float64 and scalar_in.dtype == torch.float64
+        L.call('dnmf_bcd_state', int(phase), state.data_ptr(), scalar_in.data_ptr(), self._stream())
+
+    def bcd_advance(self, X, Xm, X_old, state, which):
+        assert X.is_contiguous() and Xm.is_contiguous() and X_old.is_contiguous()
+        L.call('dnmf_bcd_advance', X.data_ptr(), Xm.data_ptr(), X_old.data_ptr(), X.numel(), state.data_ptr(), int(which),
+               _DT[X.dtype], self._stream())
+
+    def bcd_keep(self, cur, kept, state):
+        assert cur.is_contiguous() and kept.is_contiguous()
+        L.call('dnmf_bcd_keep', cur.data_ptr(), kept.data_ptr(), cur.numel(), state.data_ptr(), _DT[cur.dtype],
+               self._stream())
 
     def div_cols(self, W, s):
         m, k = W.shape

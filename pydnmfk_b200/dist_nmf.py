@@ -75,56 +75,68 @@ class _AlgBase:
         else:
             raise Exception('Not a valid norm: Choose (fro/kl)')
 
-    # ---- BCD scalar logic shared by both grids (dist_nmf.py:503-579, :971-1047) -----------------
-    def _bcd_loop(self, itr):
+    # ---- BCD shared by both grids (dist_nmf.py:503-579, :971-1047) ---------------------------------
+    # The Lipschitz bounds, objective, momentum weights and the accept / restore decision live in a float64 device
+    # vector (csrc/dnmf_bcd.cu): one iteration is a fixed sequence of launches with no host round trip, replayed as a
+    # CUDA graph.  H_old H_old^T and A H_old^T of the restore branch are the copies kept when H_old was accepted.
+    def bcd_begin(self):
+        """initWandH (dist_nmf.py:482-501 / :951-969): scale the factors, form H H^T and A H^T, obj_old = ||A||^2 / 2."""
         ops = self.ops
         W, H = self._W(), self._H()
-        Xnorm = self._sqnorm_global(self.A_ij)
-        nW = self._sqnorm_global(W, 'w')
-        nH = self._sqnorm_global(H, 'h')
-        scale = np.sqrt(np.sqrt(Xnorm))
-        W_old = torch.empty_like(W)
-        H_old = torch.empty_like(H)
-        ops.axpby(W_old, W, W, scale / np.sqrt(nW), 0.0)
-        ops.axpby(H_old, H, H, scale / np.sqrt(nH), 0.0)
-        Wm, Hm = W_old.clone(), H_old.clone()
-        HHT = self._gram_H(H_old)
-        AHT = self._AH(H_old)
-        obj_old = 0.5 * Xnorm
+        Xnorm = self._sqnorm_dev(self.A_ij)
+        nW = float(self._sqnorm_dev(W, 'w').item())
+        nH = float(self._sqnorm_dev(H, 'h').item())
+        scale = np.sqrt(np.sqrt(float(Xnorm.item())))
+        b = self._bcd = type('BcdState', (), {})()
+        b.W_old, b.H_old = torch.empty_like(W), torch.empty_like(H)
+        ops.axpby(b.W_old, W, W, scale / np.sqrt(nW), 0.0)
+        ops.axpby(b.H_old, H, H, scale / np.sqrt(nH), 0.0)
+        b.Wm, b.Hm = b.W_old.clone(), b.H_old.clone()
+        b.HHT = self._gram_H(b.H_old)
+        b.AHT = self._AH(b.H_old)
+        b.HHT_kept, b.AHT_kept = b.HHT.clone(), b.AHT.clone()
+        b.state = torch.zeros(16, dtype=torch.float64, device=W.device)
+        ops.bcd_state(0, b.state, Xnorm)
         self.params.rw = 1
-        t_old = 1.0
-        HHTnorm = 1.0
-        WTWnorm = 1.0
-        for _ in range(itr):
-            HHTnorm_old = HHTnorm
-            HHTnorm = _sqrt_host(ops.sqnorm(HHT))
-            ops.bcd_pg_w(W, Wm, AHT, HHT, HHTnorm)
-            wsum = self._colsum_W(W, force=False)
-            ops.div_cols(W, wsum)
-            WTW = self._gram_W(W)
-            WTWnorm_old = WTWnorm
-            WTWnorm = _sqrt_host(ops.sqnorm(WTW))
-            WTA, yT = self._WTA(W)
-            ops.bcd_pg_h(H, Hm, WTA, WTW, WTWnorm, y_transposed=yT)
-            HHT = self._gram_H(H)
-            AHT = self._AH(H)
-            obj = 0.5 * self._residual_global(W, H)[0]
-            t = (1 + np.sqrt(1 + 4 * t_old ** 2)) / 2
-            if obj >= obj_old:
-                Wm.copy_(W_old)
-                Hm.copy_(H_old)
-                HHT = self._gram_H(H_old)
-                AHT = self._AH(H_old)
+
+    def bcd_step(self):
+        """One iteration of dist_nmf.py:996-1047 on the device-resident state."""
+        ops, b = self.ops, self._bcd
+        W, H = self._W(), self._H()
+        ops.bcd_state(1, b.state, ops.sqnorm(b.HHT))
+        ops.bcd_pg_w_dev(W, b.Wm, b.AHT, b.HHT, b.state, 0)
+        ops.div_cols(W, self._colsum_W(W, force=False))
+        WTW = self._gram_W(W)
+        ops.bcd_state(2, b.state, ops.sqnorm(WTW))
+        WTA, yT = self._WTA(W)
+        ops.bcd_pg_h_dev(H, b.Hm, WTA, WTW, b.state, 2, y_transposed=yT)
+        HHT = self._gram_H(H)
+        AHT, res = self._AH_and_residual(W, H)
+        b.HHT.copy_(HHT)
+        b.AHT.copy_(AHT)
+        ops.bcd_state(3, b.state, res)
+        ops.bcd_advance(W, b.Wm, b.W_old, b.state, 0)
+        ops.bcd_advance(H, b.Hm, b.H_old, b.state, 1)
+        ops.bcd_keep(b.HHT, b.HHT_kept, b.state)
+        ops.bcd_keep(b.AHT, b.AHT_kept, b.state)
+
+    def _AH_and_residual(self, W, H):
+        """A H^T and the global ||A - W H||^2 (float64 device scalar in element 0)."""
+        return self._AH(H), self._residual_global(W, H)
+
+    def _bcd_loop(self, itr):
+        from .graphs import StepGraphs, graphs_enabled
+        self.bcd_begin()
+        use_graph = itr >= 4 and graphs_enabled(self.comm1, 'mu') and getattr(self.params, 'cuda_graph', True)
+        sg = None
+        for i in range(itr):
+            if use_graph and i >= 1:
+                if sg is None:
+                    sg = StepGraphs(self.bcd_step, lambda: None)
+                sg.plain()
             else:
-                w = (t_old - 1) / t
-                ww = min(w, self.params.rw * np.sqrt(HHTnorm_old / HHTnorm))
-                wh = min(w, self.params.rw * np.sqrt(WTWnorm_old / WTWnorm))
-                ops.axpby(Wm, W, W_old, 1.0 + ww, -ww)
-                ops.axpby(Hm, H, H_old, 1.0 + wh, -wh)
-                W_old.copy_(W)
-                H_old.copy_(H)
-                t_old = t
-                obj_old = obj
+                self.bcd_step()
+        sg = None
 
 
 class nmf_algorithms_2D(_AlgBase):
@@ -305,11 +317,19 @@ class nmf_algorithms_2D(_AlgBase):
 
     def _residual_global(self, W, H):
         W_i, H_j = self._gather_W(W), self._gather_H(H)
-        r = self.comm1.allreduce_(self.ops.residual_sqnorm(self.A_ij, W_i, H_j))
-        return r.cpu().numpy()
+        return self.comm1.allreduce_(self.ops.residual_sqnorm(self.A_ij, W_i, H_j))
+
+    def _sqnorm_dev(self, X, which=None):
+        return self.comm1.allreduce_(self.ops.sqnorm(X))
+
+    def _AH_and_residual(self, W, H):
+        W_i, H_j = self._gather_W(W), self._gather_H(H)
+        V, res = self.ops.ah_residual(self.A_ij, W_i, H_j)
+        return self.cartesian1d_column.reduce_scatter_rows(V, self._w_sizes), self.comm1.allreduce_(res)
 
     def initWandH(self):
-        raise NotImplementedError('folded into FRO_BCD_update (dist_nmf.py:482-501)')
+        """dist_nmf.py:482-501: scaled factors, H H^T, A H^T and obj_old, left on the device (see bcd_begin)."""
+        self.bcd_begin()
 
     def FRO_BCD_update(self, W_update=True, itr=1000):
         """dist_nmf.py:503-579 (its own ``itr`` loop; ignores W_update)."""
@@ -495,11 +515,20 @@ class nmf_algorithms_1D(_AlgBase):
         return self.comm1.allreduce_(s) if self.p_r != 1 else s
 
     def _residual_global(self, W, H):
-        r = self.comm1.allreduce_(self.ops.residual_sqnorm(self.A_ij, W, H))
-        return r.cpu().numpy()
+        return self.comm1.allreduce_(self.ops.residual_sqnorm(self.A_ij, W, H))
+
+    def _sqnorm_dev(self, X, which=None):
+        sq = self.ops.sqnorm(X)
+        p = {None: -1, 'w': self.p_r, 'h': self.p_c}[which]
+        return self.comm1.allreduce_(sq) if p != 1 else sq
+
+    def _AH_and_residual(self, W, H):
+        V, res = self.ops.ah_residual(self.A_ij, W, H)
+        return (self.comm1.allreduce_(V) if self.p_c != 1 else V), self.comm1.allreduce_(res)
 
     def initWandH(self):
-        raise NotImplementedError('folded into FRO_BCD_update (dist_nmf.py:951-969)')
+        """dist_nmf.py:951-969: scaled factors, H H^T, A H^T and obj_old, left on the device (see bcd_begin)."""
+        self.bcd_begin()
 
     def FRO_BCD_update(self, W_update=True, itr=1000):
         """dist_nmf.py:971-1047."""

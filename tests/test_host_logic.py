@@ -268,3 +268,28 @@ def test_transform_H_index_orders_shards_by_block_column():
             cols[r] = list(range(c0 + s, c0 + e))                                # sub-block i of block column j
         order = transform_H_index((p_r, p_c)).rankidx2blkidx()
         assert sum((cols[r] for r in order), []) == list(range(n))
+
+
+def test_bench_cpu_arm_allreduce_matches_oracle():
+    """bench.py's CPU arm runs one forked process per rank and all-reduces through shared memory; its factors must be
+    the oracle's own virtual-rank result for the same shards (float32 summation order aside)."""
+    import bench
+    from oracle import nmf_oracle as O
+    m, n, k, cores, steps = 96, 64, 4, 3, 3
+    for norm in ('fro', 'kl'):
+        got = bench.cpu_probe(m, n, k, norm, steps, cores)
+        shard = m // cores
+        st = O._State()
+        st.grid, st.k, st.norm, st.method, st.W_update = O.VGrid(cores, 1), k, norm, 'mu', True
+        st.A = [np.random.default_rng(1234 + r).random((shard, n), dtype=np.float32) for r in range(cores)]
+        st.dt, st.eps, st.topo = np.dtype(np.float32), np.finfo(np.float32).eps, '1d'
+        st.W = [np.random.RandomState(11 + r).rand(shard, k).astype(np.float32) for r in range(cores)]
+        H0 = np.random.RandomState(7).rand(k, n).astype(np.float32)
+        st.H = [H0.copy() for _ in range(cores)]
+        for i in range(steps):
+            O.update(st, 1)
+            if i % 10 == 0:
+                st.H = [np.maximum(h, st.eps) for h in st.H]
+                st.W = [np.maximum(w, st.eps) for w in st.W]
+        for r, W, H in got:
+            assert np.allclose(W, st.W[r], rtol=2e-5, atol=1e-7) and np.allclose(H, st.H[r], rtol=2e-5, atol=1e-7)

@@ -151,3 +151,43 @@ def test_kl_deterministic(ops):
     W = torch.rand((4096, 32), device='cuda') + 0.1
     assert torch.equal(ops.kl_uht(A, W, H, 1e-7), ops.kl_uht(A, W, H, 1e-7))
     assert torch.equal(ops.kl_wtu(A, W, H, 1e-7), ops.kl_wtu(A, W, H, 1e-7))
+
+
+@pytest.mark.parametrize('m,n,k', [(2048, 1536, 32), (4096, 1024, 16), (515, 2052, 10), (1000, 1000, 32)])
+def test_ah_residual_fused_pass(ops, m, n, k):
+    """dnmf_ah_residual: V = A H^T together with ||A - W H||^2 and ||A||^2 in one tcgen05 pass (tc_kl_kernel<3>), against
+    float64 numpy and against the two separate passes."""
+    from pydnmfk_b200 import _lib as L
+    rs = np.random.RandomState(m + n + k)
+    A, W, H = rs.rand(m, n).astype(np.float32), rs.rand(m, k).astype(np.float32), rs.rand(k, n).astype(np.float32)
+    L.pass_count(True, reset=True)
+    L.pass_count(False, reset=True)
+    V, res = ops.ah_residual(_dev(A), _dev(W), _dev(H))
+    torch.cuda.synchronize()
+    assert L.pass_count(True) == 1 and L.pass_count(False) == 0, 'fused pass did not take the tcgen05 kernel'
+    f = np.float64
+    Vr = A.astype(f) @ H.astype(f).T
+    rr = np.linalg.norm(A.astype(f) - W.astype(f) @ H.astype(f)) ** 2
+    ar = np.linalg.norm(A.astype(f)) ** 2
+    assert T.rel_fro(V.cpu().numpy(), Vr) < 2e-6
+    got = res.cpu().numpy()
+    assert abs(got[0] - rr) <= 2e-6 * rr and abs(got[1] - ar) <= 1e-6 * ar, (got, rr, ar)
+    sep = ops.residual_sqnorm(_dev(A), _dev(W), _dev(H)).cpu().numpy()
+    assert abs(got[0] - sep[0]) <= 2e-6 * rr and abs(got[1] - sep[1]) <= 1e-6 * ar
+
+
+def test_residual_on_the_tensor_pipeline(ops):
+    """tc_kl_kernel<2> (dnmf_set_tc_residual(1)) against the CUDA-core residual kernel and float64 numpy."""
+    from pydnmfk_b200 import _lib as L
+    rs = np.random.RandomState(5)
+    m, n, k = 2048, 2048, 32
+    A, W, H = rs.rand(m, n).astype(np.float32), rs.rand(m, k).astype(np.float32), rs.rand(k, n).astype(np.float32)
+    ref = ops.residual_sqnorm(_dev(A), _dev(W), _dev(H)).cpu().numpy()
+    L.call('dnmf_set_tc_residual', 1)
+    try:
+        got = ops.residual_sqnorm(_dev(A), _dev(W), _dev(H)).cpu().numpy()
+    finally:
+        L.call('dnmf_set_tc_residual', 0)
+    f = np.float64
+    rr = np.linalg.norm(A.astype(f) - W.astype(f) @ H.astype(f)) ** 2
+    assert abs(got[0] - rr) <= 2e-6 * rr and abs(got[0] - ref[0]) <= 2e-6 * rr and abs(got[1] - ref[1]) <= 1e-6 * ref[1]
