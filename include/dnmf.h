@@ -348,6 +348,15 @@ int dnmf_xchg_update_h(void* const* bases, int nranks, int me, int mode, void* H
                        const void* aux, int64_t n, int64_t k, double p0, int clamp, int dtype, void* stream);
 int dnmf_xchg_error(const void* local_region, int* error_out, void* stream);
 
+/* HALS W sweep (dist_nmf.py:888-893, 2-D :427-432) as ONE cooperative launch: the k Gauss-Seidel column updates with
+ * their k dependent global norms (utils.py:388-391) run inside a persistent grid; block partials are summed in a fixed
+ * order behind a grid barrier and, for nranks > 1, the per-rank sums travel through the peers' exchange regions
+ * (bases, as in dnmf_xchg_update_h; xchg_n = the n the regions were sized for) instead of k all-reduces.
+ * scratch: k * 1024 doubles + 256 bytes of device memory, zeroed once by the caller (the kernel leaves it zeroed). */
+int dnmf_hals_w_sweep(void* W, int64_t ldw, const void* V, int64_t ldv, const void* G, int64_t m, int64_t k, double eps,
+                      void* const* bases, int nranks, int me, int64_t xchg_n, void* scratch, int64_t scratch_bytes, int dtype,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,7 @@ SIGNATURES = {
     'dnmf_xchg_bytes': (i64, [i32, i64, i64, i32]),
     'dnmf_xchg_error': (i32, [vp, C.POINTER(i32), vp]),
     'dnmf_xchg_update_h': (i32, [C.POINTER(vp), i32, i32, i32, vp, i64, vp, i64, vp, i64, i64, dbl, i32, i32, vp]),
+    'dnmf_hals_w_sweep': (i32, [vp, i64, vp, i64, vp, i64, i64, dbl, C.POINTER(vp), i32, i32, i64, vp, i64, i32, vp]),
     'dnmf_mu_fit_resident_smem_bytes': (i64, [i64, i64, i64, i32, i32]),
     'dnmf_mu_fit_resident_cluster_size': (i32, [i64, i64, i64, i32, i32]),
     'dnmf_mu_fit_resident': (i32, [vp, i64, vp, vp, i64, i64, i64, i64, i32, i32, i64, i64, dbl, i32, vp]),

@@ -107,9 +107,11 @@ struct XchgCtrl {                       // at offset 0 of every rank's region
   unsigned int done_push, done_upd;     // CTA completion counters of the local kernels
   unsigned int epoch;                   // exchanges started so far on this rank
   unsigned int error;                   // != 0: a wait timed out (peer died); results are invalid
+  unsigned int hals_epoch;              // HALS W sweeps run so far on this rank
+  unsigned int grid_bar;                // grid barrier counter of the sweep kernel (zeroed by its last block)
 };
 struct XchgLayout {
-  int64_t n_chunk, off_recv, off_aux, off_stage, bytes;
+  int64_t n_chunk, off_recv, off_aux, off_stage, off_hals_sum, off_hals_flag, bytes;
 };
 XchgLayout xchg_layout(int P, int64_t n, int64_t k, int dtype) {
   XchgLayout L;
@@ -118,7 +120,9 @@ XchgLayout xchg_layout(int P, int64_t n, int64_t k, int dtype) {
   L.off_recv = 256;
   L.off_aux = L.off_recv + round_up((int64_t)P * L.n_chunk * k * es, 256);
   L.off_stage = L.off_aux + round_up((int64_t)P * k * k * es, 256);
-  L.bytes = L.off_stage + round_up(k * n * es, 256);
+  L.off_hals_sum = L.off_stage + round_up(k * n * es, 256);                  // [DNMF_MAX_K][XCHG_MAX_P] float64
+  L.off_hals_flag = L.off_hals_sum + DNMF_MAX_K * XCHG_MAX_P * 8;             // [DNMF_MAX_K][XCHG_MAX_P] uint32
+  L.bytes = L.off_hals_flag + DNMF_MAX_K * XCHG_MAX_P * 4;
   return L;
 }
 struct XchgBases { char* p[XCHG_MAX_P]; };
@@ -275,6 +279,99 @@ __global__ void __launch_bounds__(256) xchg_finish_kernel(XchgBases B, XchgLayou
   }
 }
 __global__ void xchg_epoch_kernel(XchgCtrl* ctrl) { ctrl->epoch += 1u; }
+
+// ---------------------------------------------------------------------------------------------------------
+// HALS W sweep in ONE launch (dist_nmf.py:888-893; 2-D :427-432): for kk = 0..k-1, Gauss-Seidel,
+//     t = W[:,kk] G[kk,kk] + V[:,kk] - W G[:,kk];  W[:,kk] = max(t, eps);  W[:,kk] /= ||W[:,kk]||_2 (global)
+// The k column norms are k dependent global reductions.  The reference (and round 1 of this library) runs them as k x
+// (kernel, reduction kernel, all-reduce, scaling kernel); here one persistent grid walks the columns, reduces the
+// block partials behind a grid barrier in a fixed order and, on a row grid, exchanges the per-rank sums through the
+// peers' exchange regions (one 8-byte store per peer and column) instead of k NCCL all-reduces.
+// The scaling of column kk is applied lazily when the row is next touched.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T, int KP>
+__global__ void __launch_bounds__(256) hals_w_sweep_kernel(T* __restrict__ W, int64_t ldw, const T* __restrict__ V, int64_t ldv,
+                                                           const T* __restrict__ G, int64_t m, int k, T eps,
+                                                           double* __restrict__ partials, unsigned int* __restrict__ gbar,
+                                                           XchgBases B, XchgLayout L, int P, int me) {
+  __shared__ T g[KP];
+  __shared__ double red[8];
+  __shared__ double s_total;
+  XchgCtrl* ctrl = P > 1 ? reinterpret_cast<XchgCtrl*>(B.p[me]) : nullptr;
+  const unsigned int epoch = P > 1 ? ctrl->hals_epoch + 1u : 0u;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  T ss_prev = T(0);
+  for (int kk = 0; kk < k; ++kk) {
+    if (threadIdx.x < KP) g[threadIdx.x] = ((int)threadIdx.x < k) ? G[threadIdx.x * k + kk] : T(0);
+    __syncthreads();
+    double sq = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < m; r += stride) {
+      T* w = W + r * ldw;
+      if (kk > 0 && ss_prev > T(0)) w[kk - 1] = w[kk - 1] / ss_prev;
+      T d = T(0);
+#pragma unroll
+      for (int l = 0; l < KP; ++l)
+        if (l < k) d = fma(w[l], g[l], d);
+      T v = w[kk] * g[kk] + V[r * ldv + kk] - d;
+      v = v > eps ? v : eps;
+      w[kk] = v;
+      sq += (double)v * (double)v;
+    }
+    const double bs = block_sum<256>(sq, red);
+    if (threadIdx.x == 0) {
+      partials[(int64_t)kk * gridDim.x + blockIdx.x] = bs;
+      __threadfence();
+      atomicAdd(gbar, 1u);
+      const unsigned int target = (unsigned int)(kk + 1) * gridDim.x;
+      while (ld_acquire_gpu(gbar) < target) {}
+      double tot = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) tot += partials[(int64_t)kk * gridDim.x + b];   // fixed order
+      if (P > 1) {
+        if (blockIdx.x == 0) {
+          for (int q = 0; q < P; ++q) {
+            double* dst = reinterpret_cast<double*>(B.p[q] + L.off_hals_sum) + kk * XCHG_MAX_P + me;
+            *reinterpret_cast<volatile double*>(dst) = tot;
+          }
+          __threadfence_system();
+          for (int q = 0; q < P; ++q)
+            st_release_sys(reinterpret_cast<unsigned int*>(B.p[q] + L.off_hals_flag) + kk * XCHG_MAX_P + me, epoch);
+        }
+        const unsigned int* flags = reinterpret_cast<const unsigned int*>(B.p[me] + L.off_hals_flag) + kk * XCHG_MAX_P;
+        const double* sums = reinterpret_cast<const double*>(B.p[me] + L.off_hals_sum) + kk * XCHG_MAX_P;
+        tot = 0.0;
+        const long long t0 = clock64();
+        for (int q = 0; q < P; ++q) {
+          while (ld_acquire_sys(flags + q) < epoch) {
+            if (clock64() - t0 > 20000000000LL) { ctrl->error = 1u; break; }
+          }
+          tot += *reinterpret_cast<const volatile double*>(sums + q);                                 // rank order
+        }
+      }
+      s_total = tot;
+    }
+    __syncthreads();
+    ss_prev = (T)sqrt(s_total);
+    __syncthreads();
+  }
+  if (ss_prev > T(0))
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < m; r += stride) W[r * ldw + (k - 1)] /= ss_prev;
+  // last block out resets the barrier counter and advances the sweep epoch for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(gbar, 1u);
+    if (done == (unsigned int)(k + 1) * gridDim.x - 1u) {
+      *gbar = 0u;
+      if (P > 1) ctrl->hals_epoch = epoch;
+    }
+  }
+}
 
 struct CommBox {
   ncclComm_t comm;
@@ -498,6 +595,52 @@ int dnmf_xchg_update_h(void* const* bases, int nranks, int me, int mode, void* H
 #undef DNMF_XCHG_T
   xchg_epoch_kernel<<<1, 1, 0, st>>>(reinterpret_cast<XchgCtrl*>(B.p[me]));
   DNMF_LAUNCH_CHECK("xchg_epoch_kernel");
+  return 0;
+}
+
+// HALS W sweep, one launch.  nranks == 1 (or bases == NULL): single rank, `scratch` must hold k * 1024 doubles + 1 uint32
+// (zeroed once by the caller; the kernel leaves it zeroed).  nranks > 1: the column norms are summed over the ranks
+// through the exchange regions `bases` (dnmf_xchg_bytes for the communicator's n, k), scratch as above.
+int dnmf_hals_w_sweep(void* W, int64_t ldw, const void* V, int64_t ldv, const void* G, int64_t m, int64_t k, double eps,
+                      void* const* bases, int nranks, int me, int64_t xchg_n, void* scratch, int64_t scratch_bytes, int dtype,
+                      void* stream) {
+  DNMF_CHECK_ARG(W && V && G && scratch, "null pointer");
+  DNMF_CHECK_ARG(dtype == DNMF_F32 || dtype == DNMF_F64, "dtype");
+  DNMF_CHECK_ARG(k >= 1 && k <= DNMF_MAX_K && m >= 0 && ldw >= k && ldv >= k, "bad shape");
+  DNMF_CHECK_ARG(nranks >= 1 && nranks <= XCHG_MAX_P && me >= 0 && me < nranks && (nranks == 1 || bases), "bad rank count");
+  DNMF_CHECK_ARG(scratch_bytes >= (int64_t)(k * 1024 * 8 + 256), "scratch too small (k * 1024 doubles + 256 bytes)");
+  if (m == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  XchgBases B;
+  for (int q = 0; q < XCHG_MAX_P; ++q) B.p[q] = (nranks > 1 && q < nranks) ? reinterpret_cast<char*>(bases[q]) : nullptr;
+  XchgLayout L = xchg_layout(nranks, xchg_n > 0 ? xchg_n : 1, k, dtype);
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
+  unsigned int* gbar = reinterpret_cast<unsigned int*>(scratch);
+  int grid = (int)std::min<int64_t>(ceil_div(m, 256), std::min<int64_t>((int64_t)sm_count() * 2, 1024));
+  const int kp = padded_k(k);
+  {
+    void* args[16];
+    int ki = (int)k;
+    float epsf = (float)eps;
+    double epsd = eps;
+    args[0] = &W; args[1] = &ldw; args[2] = &V; args[3] = &ldv; args[4] = &G; args[5] = &m; args[6] = &ki;
+    args[7] = dtype == DNMF_F32 ? (void*)&epsf : (void*)&epsd;
+    args[8] = &partials; args[9] = &gbar; args[10] = &B; args[11] = &L; args[12] = &nranks; args[13] = &me;
+    const void* fn = nullptr;
+#define DNMF_HALS_FN(T) DNMF_DISPATCH_KP(kp, { fn = (const void*)hals_w_sweep_kernel<T, KP>; })
+    if (dtype == DNMF_F32) { DNMF_HALS_FN(float); }
+    else { DNMF_HALS_FN(double); }
+#undef DNMF_HALS_FN
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "hals_w_sweep occupancy");
+    const int cap = per_sm * sm_count();
+    if (cap < 1) return fail(DNMF_E_UNSUPPORTED, "hals_w_sweep: kernel does not fit on an SM");
+    if (grid > cap) grid = cap;
+    e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, st);     // co-residency guaranteed
+    if (e != cudaSuccess) return cuda_fail(e, "hals_w_sweep_kernel");
+    tls().launches++;
+  }
   return 0;
 }
 

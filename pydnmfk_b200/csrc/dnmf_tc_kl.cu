@@ -18,8 +18,9 @@
 // rows of A like MODE 0, U = A itself (so GEMM2 yields V = A H^T exactly as the FRO kernel does), and the splitters
 // accumulate the residual terms on the side.
 //
-// Warp roles (512 threads, one persistent CTA per SM): w0 A-TMA | w1 MMA issuer | w2-5, w11-14 splitter groups |
-// w6-9 drain | w10 Bcat-TMA (lane 0) + Fr-TMA (lane 1) | w15 GEMM1 issuer.
+// Warp roles (one persistent CTA per SM, warpgroup-aligned so that setmaxnreg can move registers between them):
+// w0 A-TMA | w1 GEMM2 issuer + TMEM owner | w2 Bcat-TMA (lane 0) + Fr-TMA (lane 1) | w3 GEMM1 issuer | w4-7 drain |
+// w8-11, w12-15 [, w16-19] splitter groups.
 #include "generic_passes.cuh"
 #include "tc_common.cuh"
 
@@ -27,7 +28,13 @@ namespace dnmf {
 namespace {
 
 constexpr int KK = 32;            // factor width handled by this kernel
-constexpr int KL_THREADS = 512;
+// KL_GROUPS splitter groups of 4 warps work on tiles round-robin; the per-tile chain (A tile -> S load -> divide -> split ->
+// tensor-memory store -> GEMM2 -> slot free) is latency-bound, so the number of tiles in flight sets the pass time.
+#ifndef KL_GROUPS
+#define KL_GROUPS 2
+#endif
+constexpr int KL_THREADS = 512 + 128 * (KL_GROUPS - 2);
+constexpr int KL_PAIRS = KL_GROUPS * 128;      // residual pairs per CTA (one per splitter thread)
 constexpr int KL_CHUNK = 4;       // K-tiles accumulated in TMEM before the drain warps fold them into registers
 
 // KL_S1 = 1: GEMM1 adds its three split terms into ONE 32-column accumulator (umma_tile_cat); the splitters then load
@@ -51,9 +58,15 @@ struct KlCfg {
   static constexpr int NBUF = 2, NT = 3, NS = 4, S_COLS = KK;
 #else
 #ifndef KL_NT
+#if KL_GROUPS == 3
+#define KL_NBUF 1
+#define KL_NT 3
+#define KL_NS 3
+#else
 #define KL_NBUF 2
 #define KL_NT 2
 #define KL_NS 3
+#endif
 #endif
   static constexpr int NBUF = KL_NBUF, NT = KL_NT, NS = KL_NS, S_COLS = 2 * KK;
 #endif
@@ -124,6 +137,14 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // With three splitter groups the CTA has 640 threads = 96 registers per thread at launch; the producer / issuer
+  // warpgroup needs far fewer and hands the rest to the splitter warpgroups (setmaxnreg works per warpgroup, hence the
+  // warpgroup-aligned roles).  setmaxnreg.inc can only draw on what the CTA's own warpgroups released (the CTA's pool is
+  // its launch allocation, 640 x 96): 4 x 32 + 4 x 80 + 12 x 120 registers x 32 lanes = 60416 <= 61440.
+  if (warp < 4) {
+#if KL_GROUPS == 3
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+#endif
   if (warp == 0) {
     // ===================== A producer =====================
     if (lane == 0) {
@@ -150,7 +171,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2) {
     // ===================== Bcat producer (lane 0, GEMM2 B operand) and FrCat producer (lane 1, GEMM1 B operand) =====
     if (lane == 0 && MODE != 2) {
       int s = 0;
@@ -183,7 +204,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 15) {
+  } else if (warp == 3) {
     // ===================== GEMM1 issuer: S = Fx . Fr^T, runs ahead of GEMM2 by up to NS tiles =====================
     //   KL_S1: cols [0,32) = Fx_hi*Fr_hi + Fx_hi*Fr_lo + Fx_lo*Fr_hi
     //   else : cols [0,32) Fx_hi*Fr_hi ; cols [32,64) Fx_hi*Fr_lo + Fx_lo*Fr_hi
@@ -225,8 +246,8 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       pxu ^= 1u;
     }
     if (prof && lane == 0) { prof[blockIdx.x * 16 + 0] = t_g1wait; prof[blockIdx.x * 16 + 1] = t_g1; }
-  } else if (warp == 1) {
-    // ===================== GEMM2 issuer (converged warp, elected lane inside the asm block) =====================
+  } else {
+    // ===================== GEMM2 issuer, warp 1 (converged warp, elected lane inside the asm block) ==============
     constexpr uint32_t idesc_full = make_idesc(N2, 0);
     constexpr uint32_t idesc_half = make_idesc(KK, 0);
     int sb = 0, ts = 0, buf = 0;
@@ -264,11 +285,15 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       prof[blockIdx.x * 16 + 2] = t_acce; prof[blockIdx.x * 16 + 3] = t_tfull; prof[blockIdx.x * 16 + 4] = t_bfull;
       prof[blockIdx.x * 16 + 5] = t_g2; prof[blockIdx.x * 16 + 15] = clock64() - t0;
     }
-  } else if (warp < 6 || (warp >= 11 && warp < 15)) {
+  }
+  } else if (warp >= 8) {
+#if KL_GROUPS == 3
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+#endif
     // ===================== splitters: A tile + S tile -> U = A / (S + eps) -> {U, U_lo} in TMEM ====================
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const int group = (warp >= 11) ? 1 : 0;
+    const int group = (warp - 8) >> 2;
     int tile = 0;
     uint32_t pxe = 0;
     double res_sum = 0.0, a_sum = 0.0;      // MODE 2 only
@@ -300,7 +325,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         pxe ^= 1u;
       }
       for (int kt = kt0; kt < kt1; ++kt, ++tile) {
-        if ((tile & 1) != group) continue;
+        if (tile % KL_GROUPS != group) continue;
         const int sa = tile % SA, ts = tile % NT, ss = tile % NS;
         const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u, ps = (uint32_t)(tile / NS) & 1u;
         TC_T(t_store);
@@ -354,9 +379,14 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #define KL_S_OF(j) __uint_as_float(s0[j])
 #else
           uint32_t s0[32], s1[32];
-          tmem_ld_x32(saddr, s0);           // Fx_hi * Fr_hi
-          tmem_ld_x32(saddr + 32, s1);      // Fx_hi * Fr_lo + Fx_lo * Fr_hi
-          tmem_ld_wait();
+          if (dbg & 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s0[j] = 0x3F800000u; s1[j] = 0u; }
+          } else {
+            tmem_ld_x32(saddr, s0);           // Fx_hi * Fr_hi
+            tmem_ld_x32(saddr + 32, s1);      // Fx_hi * Fr_lo + Fx_lo * Fr_hi
+            tmem_ld_wait();
+          }
 #define KL_S_OF(j) (__uint_as_float(s0[j]) + __uint_as_float(s1[j]))
 #endif
           if (MODE == 2 || MODE == 3) {
@@ -407,13 +437,15 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #endif
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::OP_COL0 + ts * 64);
-        tmem_st_x32(taddr, u);
-        tmem_st_x32(taddr + 32, lo);
+        if (!(dbg & 0x80)) {
+          tmem_st_x32(taddr, u);
+          tmem_st_x32(taddr + 32, lo);
+        }
 #if !TC_EARLY_RELEASE
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iAE + sa));          // smem tile fully consumed (see dnmf_tc.cu)
 #endif
-        tmem_st_wait();
+        if (!(dbg & 0x80)) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iTF + ts));
@@ -421,16 +453,19 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     if (MODE == 2 || MODE == 3) {
       // one (residual, norm) pair per splitter thread; summed in a fixed order by the caller
-      double* pairs = pairs_out + ((int64_t)blockIdx.x * 256 + (group * 4 + q) * 32 + lane) * 2;
+      double* pairs = pairs_out + ((int64_t)blockIdx.x * KL_PAIRS + (group * 4 + q) * 32 + lane) * 2;
       pairs[0] = res_sum;
       pairs[1] = a_sum;
     }
-    if (prof && warp == 2 && lane == 0) {
+    if (prof && warp == 8 && lane == 0) {
       prof[blockIdx.x * 16 + 6] = t_afull; prof[blockIdx.x * 16 + 7] = t_load; prof[blockIdx.x * 16 + 8] = t_sfull;
       prof[blockIdx.x * 16 + 9] = t_div; prof[blockIdx.x * 16 + 10] = t_tfree; prof[blockIdx.x * 16 + 11] = t_store;
     }
   } else {
-    // ===================== drain warps 6-9 =====================
+#if KL_GROUPS == 3
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+#endif
+    // ===================== drain warps 4-7 =====================
     const int q = warp & 3;
     int buf = 0;
     uint32_t accphase = 0;
@@ -631,7 +666,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
 // ws = [Bcat | FrCat | partials | pairs (grid x 256 x 2 float64)]
 int64_t tc_ah_residual_workspace_bytes(int64_t m, int64_t n) {
   const KlPlan p = kl_plan(0, m, n);
-  return p.base.bcat_bytes + p.frcat_bytes + p.base.partial_bytes + round_up((int64_t)p.base.grid * 256 * 2 * (int64_t)sizeof(double), 1024);
+  return p.base.bcat_bytes + p.frcat_bytes + p.base.partial_bytes + round_up((int64_t)p.base.grid * KL_PAIRS * 2 * (int64_t)sizeof(double), 1024);
 }
 
 int tc_ah_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* V,
@@ -678,7 +713,7 @@ int tc_ah_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw,
   reduce_partials_kernel<float><<<(unsigned)ceil_div(m * k, 256), 256, 0, st>>>(P, split_stride, pl.splits, m, k, V, ldv, 1, KK);
   DNMF_LAUNCH_CHECK("reduce_partials_kernel");
   *out_pairs = pairs;
-  *n_pairs = (int64_t)pl.grid * 256;
+  *n_pairs = (int64_t)pl.grid * KL_PAIRS;
   return 0;
 }
 
@@ -695,7 +730,7 @@ void tc_set_residual(int on) { g_tc_residual = on ? 1 : 0; }
 
 int64_t tc_residual_workspace_bytes(int64_t m, int64_t n) {
   const KlPlan p = kl_plan(0, m, n);
-  return p.frcat_bytes + round_up((int64_t)p.base.grid * 256 * 2 * (int64_t)sizeof(double), 1024);
+  return p.frcat_bytes + round_up((int64_t)p.base.grid * KL_PAIRS * 2 * (int64_t)sizeof(double), 1024);
 }
 
 int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, int64_t m,
@@ -730,7 +765,7 @@ int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, co
                                                         0, pairs, tc_prof_ptr());
   DNMF_LAUNCH_CHECK("tc_kl_kernel<2>");
   *out_pairs = pairs;
-  *n_pairs = (int64_t)pl.grid * 256;
+  *n_pairs = (int64_t)pl.grid * KL_PAIRS;
   return 0;
 }
 

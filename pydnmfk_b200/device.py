@@ -285,6 +285,21 @@ class DeviceOps:
                sq.data_ptr(), _DT[W.dtype], ws, wsb, self._stream())
         return sq
 
+    def hals_w_sweep(self, W, V, G, eps, peer=None):
+        """All k column updates of the HALS W sweep (+ their global norms) in one cooperative launch; `peer` = the
+        PeerExchange of a row grid (column norms summed over the ranks through peer memory) or None (one rank)."""
+        m, k = W.shape
+        need = k * 1024 * 8 + 256
+        if getattr(self, '_hals_scratch', None) is None or self._hals_scratch.numel() < need:
+            self._hals_scratch = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        sc = self._hals_scratch
+        if peer is None:
+            bases, P, me, xn = None, 1, 0, 0
+        else:
+            bases, P, me, xn = peer._bases, peer.P, peer.me, peer.n
+        L.call('dnmf_hals_w_sweep', W.data_ptr(), _ld(W), V.data_ptr(), _ld(V), G.data_ptr(), m, k, float(eps), bases, P, me,
+               xn, sc.data_ptr(), sc.numel(), _DT[W.dtype], self._stream())
+
     def div_col(self, W, kk, ss_sq):
         L.call('dnmf_div_col', W.data_ptr(), _ld(W), W.shape[0], kk, ss_sq.data_ptr(), _DT[W.dtype], self._stream())
 

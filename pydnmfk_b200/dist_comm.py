@@ -317,7 +317,14 @@ class Comm:
                 # cached by member list, so repeated fits re-use them instead of leaking one per MPI_comm.
                 gkey = tuple(members)
                 if gkey not in _group_cache:
-                    _group_cache[gkey] = dist.new_group(ranks=members)
+                    if members == self._ranks and self._group is not None:
+                        _group_cache[gkey] = self._group          # the sub-communicator spans this whole communicator
+                    elif self.size == dist.get_world_size():
+                        _group_cache[gkey] = dist.new_group(ranks=members)
+                    else:
+                        # a grid inside a replica group (NMFk ensemble spread over groups of ranks): only the members
+                        # of this communicator get here, so the creation must not wait for the rest of the world
+                        _group_cache[gkey] = dist.new_group(ranks=members, use_local_synchronization=True)
                 group = _group_cache[gkey]
             if bkey == mine:
                 ckey = (tuple(members), tuple(self._dims[d] for d in keep))
@@ -329,6 +336,25 @@ class Comm:
 
     def Free(self):
         pass
+
+
+def split_into_groups(world, group_size):
+    """Consecutive blocks of ``group_size`` world ranks as communicators (collective over ``world``: every rank creates
+    every group, in the same order); returns (this rank's group communicator, group index, number of groups)."""
+    assert world.size % group_size == 0
+    n_groups = world.size // group_size
+    mine = None
+    for g in range(n_groups):
+        members = [world.ranks[g * group_size + j] for j in range(group_size)]
+        gkey = tuple(members)
+        if group_size > 1 and dist.is_available() and dist.is_initialized() and gkey not in _group_cache:
+            _group_cache[gkey] = dist.new_group(ranks=members)
+        if g == world.rank // group_size:
+            ckey = (gkey, None)
+            if ckey not in _comm_cache:
+                _comm_cache[ckey] = Comm(members, _group_cache.get(gkey))
+            mine = _comm_cache[ckey]
+    return mine, world.rank // group_size, n_groups
 
 
 class _MPI:

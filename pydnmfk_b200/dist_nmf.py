@@ -471,6 +471,11 @@ class nmf_algorithms_1D(_AlgBase):
         """dist_nmf.py:873-893."""
         HHT = self._gram_H(self.H_j)
         AH = self._AH(self.H_j)
+        if self.p_r == 1 or self._px is not None:
+            # one cooperative launch for the whole sweep; on a row grid the k column norms cross the ranks through
+            # peer memory inside the kernel instead of k all-reduces
+            self.ops.hals_w_sweep(self.W_i, AH, HHT, self.eps, peer=self._px if self.p_r != 1 else None)
+            return
         for kk in range(self.k):
             sq = self.ops.hals_w_col(self.W_i, AH, HHT, kk, self.eps)
             if self.p_r != 1:

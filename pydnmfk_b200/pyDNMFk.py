@@ -83,12 +83,17 @@ class PyNMFk():
         self.params = params
         self.comm1 = self.params.comm1
         self.rank = self.comm1.rank
+        if getattr(self.params, 'grid', None):                       # pyDNMFk.py:132-135: params.grid wins over p_r / p_c
+            self.params.p_r, self.params.p_c = self.params.grid[0], self.params.grid[1]
+        if getattr(self.params, 'k_range', None):                    # pyDNMFk.py:156-160
+            self.params.start_k, self.params.end_k = self.params.k_range[0], self.params.k_range[1]
         self.p_r, self.p_c = self.params.p_r, self.params.p_c
         self.fpath = var_init(self.params, 'fpath', default='data/')
         self.fname = var_init(self.params, 'fname', default='A_')
         self.p = self.p_r * self.p_c
         self.start_k = var_init(self.params, 'start_k', default=1)
         self.end_k = var_init(self.params, 'end_k', default=10)
+        self.params.start_k, self.params.end_k = self.start_k, self.end_k      # pvalueAnalysis reads them back
         self.step_k = var_init(self.params, 'step_k', default=1)
         self.sill_thr = var_init(self.params, 'sill_thr', default=0.9)
         self.verbose = var_init(self.params, 'verbose', default=False)
@@ -116,21 +121,25 @@ class PyNMFk():
         self._numpy_in = not isinstance(self.A_ij, torch.Tensor)
 
     def _spread(self):
-        return (bool(getattr(self.params, 'ensemble_parallel', False)) and self.params.comm1.size > 1
-                and self.p_r * self.p_c == 1)
+        """Replica mode: ``params.ensemble_parallel`` and a world larger than the p_r x p_c factorization grid.  The
+        world is cut into ``world.size / (p_r p_c)`` replica groups; every group holds the whole matrix on its own
+        grid and takes every n_groups-th perturbation (no data-path collective between groups)."""
+        world = self.comm1
+        return (bool(getattr(self.params, 'ensemble_parallel', False)) and world.size > self.p
+                and world.size % self.p == 0)
 
-    def _enter_solo(self):
-        """Swap the communicators on ``params`` for a private size-1 grid (replica mode)."""
-        from .dist_comm import Comm, MPI_comm
-        world = self.params.comm1
+    def _enter_group(self):
+        """Swap the communicators on ``params`` for this rank's replica group (a private p_r x p_c grid)."""
+        from .dist_comm import MPI_comm, split_into_groups
+        world = self.comm1
         saved = (self.params.comm1, self.params.comm, self.params.row_comm, self.params.col_comm)
-        solo = Comm([world.ranks[world.rank]], None)
-        grid = MPI_comm(solo, 1, 1)
-        self.params.comm1, self.params.comm = solo, grid
+        gcomm, self._group_index, self._n_groups = split_into_groups(world, self.p)
+        grid = MPI_comm(gcomm, self.p_r, self.p_c)
+        self.params.comm1, self.params.comm = gcomm, grid
         self.params.row_comm, self.params.col_comm = grid.cart_1d_row(), grid.cart_1d_column()
         return saved
 
-    def _leave_solo(self, saved):
+    def _leave_group(self, saved):
         self.params.comm1, self.params.comm, self.params.row_comm, self.params.col_comm = saved
 
     def fit_ensemble(self, k):
@@ -149,8 +158,8 @@ class PyNMFk():
         todo = list(range(self.perturbations))
         saved = None
         if spread:
-            todo = todo[world.rank::world.size]
-            saved = self._enter_solo()
+            saved = self._enter_group()
+            todo = todo[self._group_index::self._n_groups]
         mine = {}
         pending = []
         for perturbation in todo:
@@ -183,10 +192,15 @@ class PyNMFk():
                 if not spread:
                     self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
         if spread:
-            self._leave_solo(saved)
+            self._leave_group(saved)
+            # every rank needs ITS block of every perturbation: take the parts of the ranks that sit at the same
+            # position of their replica group
+            pos = world.rank % self.p
             merged = {}
-            for part in world.allgather({p: (W.cpu().numpy(), H.cpu().numpy(), e) for p, (W, H, e) in mine.items()}):
-                merged.update(part)
+            parts = world.allgather((pos, {p: (W.cpu().numpy(), H.cpu().numpy(), e) for p, (W, H, e) in mine.items()}))
+            for other_pos, part in parts:
+                if other_pos == pos:
+                    merged.update(part)
             mine = {p: (D.to_device(W), D.to_device(H), e) for p, (W, H, e) in merged.items()}
         results = [mine[p] for p in range(self.perturbations)]
         # Wall[:, :, p] = W_p (hstack + reshape(order='F'), pyDNMFk.py:234-235); Hall is the reference's vstack followed
@@ -203,12 +217,12 @@ class PyNMFk():
         """W-fixed fit from the cluster medians (pyDNMFk.py:245-248): only the H half-step runs.  In replica mode
         every rank runs the same (deterministic) fit on its own copy."""
         self.params.W_update = False
-        saved = self._enter_solo() if self._spread() else None
+        saved = self._enter_group() if self._spread() else None
         reg = PyNMF(self._A_dev, factors=[AvgW, AvgH], params=self.params)
         W, H, err = reg.fit()
         self.col_err = reg.column_err()
         if saved is not None:
-            self._leave_solo(saved)
+            self._leave_group(saved)
         return W.cpu().numpy(), H.cpu().numpy(), err
 
     @comm_timing()
@@ -226,12 +240,12 @@ class PyNMFk():
         self.params.flag = 1
         self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
         spread = self._spread()
-        saved = self._enter_solo() if spread else None               # replica mode: every rank clusters its full copy
+        saved = self._enter_group() if spread else None              # replica mode: every group clusters its own copy
         clusters = custom_clustering(self._Wall_dev, self._Hall_dev, self.params)
         [processAvg, processSTD, Hall_dev, self.clusterSilhouetteCoefficients, self.avgSilhouetteCoefficients,
          idx] = clusters.fit()
         if saved is not None:
-            self._leave_solo(saved)
+            self._leave_group(saved)
         self._Hall_dev = Hall_dev
         self.Hall = Hall_dev.cpu().numpy()
         self.params.flag = 2
@@ -243,10 +257,20 @@ class PyNMFk():
         cluster_stats = {'clusterSilhouetteCoefficients': self.clusterSilhouetteCoefficients,
                          'avgSilhouetteCoefficients': self.avgSilhouetteCoefficients, 'L_errDist': self.L_errDist,
                          'L_err': self.col_err, 'avgErr': self.avgErr, 'recon_err': self.recon_err, 'AIC': self.AIC}
-        if not spread or self.rank == 0:
+        if not spread:
             data_writer = data_write(self.params)
             data_writer.save_factors([self.AvgW, self.AvgH], reg=True)
             data_writer.save_cluster_results(cluster_stats)
+        else:
+            # every replica group holds the same (deterministic) regression factors: group 0 writes them, with ITS
+            # communicator on params -- save_factors ends in a barrier over params.comm1, which must only span the
+            # ranks that call it
+            saved = self._enter_group()
+            if self._group_index == 0:
+                data_writer = data_write(self.params)
+                data_writer.save_factors([self.AvgW, self.AvgH], reg=True)
+                data_writer.save_cluster_results(cluster_stats)
+            self._leave_group(saved)
         self.params.flag = 3
         self.cp._save_checkpoint(self.params.flag, perturbation, self.k)
 

@@ -246,3 +246,21 @@ def test_nmfk_end_to_end_matches_reference(gold, case):
                 assert abs(float(o['k%d/AIC' % k]) - float(g('AIC'))) <= 1e-3 * abs(float(g('AIC')))
             tolf = 2e-2 if loose else 2e-3
             assert T.rel_fro(o['k%d/W_reg' % k], g('W_reg')) <= tolf and T.rel_fro(o['k%d/H_reg' % k], g('H_reg')) <= tolf
+
+
+@pytest.mark.parametrize('name,world', [('wtsi_1x1_rand', 2), ('wtsi_2x1_rand', 4)])
+def test_nmfk_ensemble_over_replica_groups_matches_reference(gold, name, world):
+    """PyNMFk.fit() end to end with params.ensemble_parallel: the world is cut into replica groups of p_r x p_c ranks,
+    each taking every n_groups-th perturbation (BASELINE.json configs[4]: "perturbation ensemble batched over
+    8 x B200").  Statistics and the selected rank must equal the sequential reference run."""
+    case = K.E2E_BY_NAME[name]
+    with tempfile.TemporaryDirectory() as tmp:
+        res = mp_util.run(world, workers.nmfk_replica_worker, (case, tmp), backend='gloo', timeout=1500)
+    for o in res:
+        assert o['nopt'] == int(gold['e2e/%s/%d/nopt' % (name, o['pos'])])
+    o = res[0]
+    for k in range(case['start_k'], case['end_k'] + 1):
+        g = lambda key: gold['e2e/%s/0/k%d/%s' % (name, k, key)]   # noqa: E731
+        assert np.allclose(o['k%d/clusterSilhouetteCoefficients' % k], g('clusterSilhouetteCoefficients'), rtol=0, atol=1e-3)
+        assert np.allclose(o['k%d/ErrTol' % k], g('ErrTol'), rtol=1e-4)
+        assert np.allclose(o['k%d/L_err' % k], g('L_err'), rtol=2e-3, atol=1e-5)

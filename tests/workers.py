@@ -1,4 +1,6 @@
 """Module-level rank functions for tests/mp_util.run (they must be importable by spawned processes)."""
+import os
+
 import numpy as np
 
 
@@ -286,6 +288,41 @@ def nmfk_e2e_worker(rank, world, case, tmp):
             wname, hname = 'W_reg_factors/W.npy', 'H_reg_factors/H_%d.npy' % rank
         out['k%d/W_reg' % k] = np.load(d + wname)
         out['k%d/H_reg' % k] = np.load(d + hname)
+    return out
+
+
+def nmfk_replica_worker(rank, world, case, tmp):
+    """PyNMFk.fit() with the perturbation ensemble spread over replica groups: the world is larger than the case's
+    p_r x p_c grid, every group of p_r * p_c ranks holds the whole matrix (params.ensemble_parallel)."""
+    import random
+    import torch
+    from oracle import nmfk_cases as K
+    from pydnmfk_b200.data_io import read_results
+    from pydnmfk_b200.dist_comm import MPI
+    from pydnmfk_b200.pyDNMFk import PyNMFk
+    from pydnmfk_b200.utils import parse
+    torch.cuda.set_device(int(os.environ.get('DNMF_TEST_DEVICE', '0')))
+    X = K.wtsi().astype('float32')
+    p_r, p_c = case['grid']
+    pos = rank % (p_r * p_c)
+    p = parse()
+    p.comm1 = MPI.COMM_WORLD
+    p.size, p.rank, p.p_r, p.p_c = world, rank, p_r, p_c
+    p.comm = p.row_comm = p.col_comm = None          # set per replica group by PyNMFk
+    p.ensemble_parallel = True
+    p.fpath, p.fname, p.ftype = 'data/', 'wtsi', 'mat'
+    p.init, p.itr, p.norm, p.method, p.verbose = case['init'], case['itr'], case['norm'], case['method'], False
+    p.start_k, p.end_k, p.step_k, p.sill_thr = case['start_k'], case['end_k'], 1, case['sill_thr']
+    p.perturbations, p.noise_var, p.sampling = case['perturbations'], case['noise_var'], 'uniform'
+    p.results_path, p.checkpoint, p.precision = tmp + '/', False, 'float32'
+    random.seed(K.NNSVD_PY_SEED)
+    nopt = PyNMFk(_block_of(X, pos, (p_r, p_c)), factors=None, params=p).fit()
+    out = dict(nopt=int(nopt), pos=pos)
+    for k in range(case['start_k'], case['end_k'] + 1):
+        d = '%s/wtsi/%d/' % (tmp, k)
+        if rank == 0:
+            for key, val in read_results(d).items():
+                out['k%d/%s' % (k, key)] = np.asarray(val, dtype=np.float64)
     return out
 
 

@@ -18,6 +18,7 @@ ap.add_argument('--k', type=int, default=32)
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--kl', action='store_true')
 ap.add_argument('--roles', action='store_true', help='print the per-warp-role cycle split of the tcgen05 kernel')
+ap.add_argument('--dbg', default='0', help='timing-ablation bits (dnmf_set_tc_debug) for the role timers')
 a = ap.parse_args()
 ops = D.default_ops()
 
@@ -69,6 +70,9 @@ if a.roles:
                 print('   %-22s %5.1f%%' % (n, 100 * v[:, i].mean() / tot))
 
 if a.roles and a.kl:
+    from pydnmfk_b200 import _lib as L
+    L.call('dnmf_set_tc_debug', int(a.dbg, 0))
+    print('role timers with debug flags', a.dbg)
     names = ['MMA gemm1 wait(Fr,S free)', 'MMA gemm1 issue', 'MMA wait acce', 'MMA wait t_full', 'MMA wait b_full', 'MMA gemm2 issue+loop',
              'split wait a_full', 'split load A', 'split wait S', 'split ldtm+div+lo', 'split wait t_free', 'split store', '', '', '', 'total']
     for nm, fn in (('kl_uht', lambda: ops.kl_uht(A, W, H, 1.2e-7)), ('kl_wtu', lambda: ops.kl_wtu(A, W, H, 1.2e-7))):
