@@ -24,7 +24,7 @@ _NMF_FLAGS = [
     ('fpath', str, 'data/', 'directory of the input'),
     ('ftype', str, 'mat', 'input format: mat / npy / csv / folder'),
     ('fname', str, 'A_', 'input file stem'),
-    ('init', str, 'rand', 'factor initialisation: rand (nnsvd: not in this build)'),
+    ('init', str, 'rand', 'factor initialisation: rand / nnsvd (nnsvd: 1-D grids only, like the reference)'),
     ('itr', int, 5000, 'update iterations'),
     ('norm', str, 'kl', 'objective: kl or fro'),
     ('method', str, 'mu', 'update rule: mu, hals or bcd'),
@@ -90,16 +90,23 @@ def main(argv=None):
     if args.process == 'pyDNMFk':
         if rank == 0:
             print('Starting PyDNMFk...')
-        nopt = PyNMFk(A_ij, factors=None, params=args).fit()
+        out = PyNMFk(A_ij, factors=None, params=args).fit()
         if rank == 0:
             print('PyDNMFk done.')
-        return nopt
-    if rank == 0:
-        print('Starting PyDNMF...')
-    W, H, err = PyNMF(A_ij, factors=None, params=args).fit()
-    if rank == 0:
-        print('PyDNMF done. relative error = %s' % err)
-    return W, H, err
+    else:
+        if rank == 0:
+            print('Starting PyDNMF...')
+        out = PyNMF(A_ij, factors=None, params=args).fit()
+        if rank == 0:
+            print('PyDNMF done. relative error = %s' % out[2])
+    if rank == 0 and args.timing_stats:
+        # reference main.py:83-88: print the per-function timings and write them as a one-row table
+        # (pandas.DataFrame([config.time]).to_csv layout); the plot of plot_results.py is out of scope
+        print(config.time)
+        keys = list(config.time.keys())
+        with open(args.results_path + 'Timing_stats.csv', 'w') as f:
+            f.write(',' + ','.join(keys) + '\n0,' + ','.join(str(config.time[key]) for key in keys) + '\n')
+    return out
 
 
 if __name__ == '__main__':

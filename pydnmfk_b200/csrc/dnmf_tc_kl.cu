@@ -34,6 +34,16 @@ constexpr int KK = 32;            // factor width handled by this kernel
 #define KL_GROUPS 2
 #endif
 constexpr int KL_THREADS = 512 + 128 * (KL_GROUPS - 2);
+// KL_WG_ALIGNED = 1: roles grouped by warpgroup (w0-3 control, w4-7 drain, w8+ splitters), which setmaxnreg needs.
+// KL_WG_ALIGNED = 0: the round-1 placement (w0 A-TMA, w1 GEMM2, w2-5 / w11-14 splitters, w6-9 drain, w10 B/F-TMA, w15 GEMM1):
+// the SM's issue arbiter prefers the higher warp id, so this one lets the GEMM1 issuer and the second splitter group win
+// ties against the first.
+#ifndef KL_WG_ALIGNED
+#define KL_WG_ALIGNED (KL_GROUPS == 3)
+#endif
+#if KL_GROUPS == 3 && !KL_WG_ALIGNED
+#error "three splitter groups need the warpgroup-aligned role placement"
+#endif
 constexpr int KL_PAIRS = KL_GROUPS * 128;      // residual pairs per CTA (one per splitter thread)
 constexpr int KL_CHUNK = 4;       // K-tiles accumulated in TMEM before the drain warps fold them into registers
 
@@ -141,7 +151,17 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // warpgroup needs far fewer and hands the rest to the splitter warpgroups (setmaxnreg works per warpgroup, hence the
   // warpgroup-aligned roles).  setmaxnreg.inc can only draw on what the CTA's own warpgroups released (the CTA's pool is
   // its launch allocation, 640 x 96): 4 x 32 + 4 x 80 + 12 x 120 registers x 32 lanes = 60416 <= 61440.
-  if (warp < 4) {
+#if KL_WG_ALIGNED
+  constexpr int W_BPROD = 2, W_G1 = 3;
+  const bool is_ctrl = warp < 4, is_split = warp >= 8;
+  const int split_group = (warp - 8) >> 2, first_split_warp = 8;
+#else
+  constexpr int W_BPROD = 10, W_G1 = 15;
+  const bool is_ctrl = warp < 2 || warp == W_BPROD || warp == W_G1;
+  const bool is_split = (warp >= 2 && warp < 6) || (warp >= 11 && warp < 15);
+  const int split_group = warp >= 11 ? 1 : 0, first_split_warp = 2;
+#endif
+  if (is_ctrl) {
 #if KL_GROUPS == 3
   asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
 #endif
@@ -171,7 +191,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == W_BPROD) {
     // ===================== Bcat producer (lane 0, GEMM2 B operand) and FrCat producer (lane 1, GEMM1 B operand) =====
     if (lane == 0 && MODE != 2) {
       int s = 0;
@@ -204,7 +224,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == W_G1) {
     // ===================== GEMM1 issuer: S = Fx . Fr^T, runs ahead of GEMM2 by up to NS tiles =====================
     //   KL_S1: cols [0,32) = Fx_hi*Fr_hi + Fx_hi*Fr_lo + Fx_lo*Fr_hi
     //   else : cols [0,32) Fx_hi*Fr_hi ; cols [32,64) Fx_hi*Fr_lo + Fx_lo*Fr_hi
@@ -286,14 +306,14 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       prof[blockIdx.x * 16 + 5] = t_g2; prof[blockIdx.x * 16 + 15] = clock64() - t0;
     }
   }
-  } else if (warp >= 8) {
+  } else if (is_split) {
 #if KL_GROUPS == 3
     asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
 #endif
     // ===================== splitters: A tile + S tile -> U = A / (S + eps) -> {U, U_lo} in TMEM ====================
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const int group = (warp - 8) >> 2;
+    const int group = split_group;
     int tile = 0;
     uint32_t pxe = 0;
     double res_sum = 0.0, a_sum = 0.0;      // MODE 2 only
@@ -457,7 +477,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       pairs[0] = res_sum;
       pairs[1] = a_sum;
     }
-    if (prof && warp == 8 && lane == 0) {
+    if (prof && warp == first_split_warp && lane == 0) {
       prof[blockIdx.x * 16 + 6] = t_afull; prof[blockIdx.x * 16 + 7] = t_load; prof[blockIdx.x * 16 + 8] = t_sfull;
       prof[blockIdx.x * 16 + 9] = t_div; prof[blockIdx.x * 16 + 10] = t_tfree; prof[blockIdx.x * 16 + 11] = t_store;
     }

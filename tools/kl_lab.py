@@ -78,14 +78,15 @@ def main():
     names = a.ops.split(',')
     for v, lib in libs.items():
         lib.dnmf_set_tc_min_elems(1)
-        lib.dnmf_set_tc_debug(0)
+        if hasattr(lib, 'dnmf_set_tc_debug'):
+            lib.dnmf_set_tc_debug(0)
         o = outs(m0, n0)
         ws, wsb = workspace(lib, m0, n0)
         for nm in names:
             run(lib, nm, dA, dW, dH, o[nm], ws, wsb)
         torch.cuda.synchronize()
         acc = {nm: float(np.linalg.norm(o[nm].cpu().numpy() - ref[nm]) / np.linalg.norm(ref[nm])) for nm in names}
-        print(json.dumps({'variant': v, 'accuracy_vs_fp64': acc, 'tc_passes': int(lib.dnmf_pass_count(1, 0))}), flush=True)
+        print(json.dumps({'variant': v, 'accuracy_vs_fp64': acc, 'tc_passes': int(lib.dnmf_pass_count(1, 0)) if hasattr(lib, 'dnmf_pass_count') else None}), flush=True)
     del dA, dW, dH
     A = torch.rand((a.m, a.n), device='cuda')
     H = torch.rand((k, a.n), device='cuda')
@@ -99,7 +100,8 @@ def main():
     for rnd in range(a.rounds + 1):
         for (v, fl, nm) in combos:
             lib = libs[v]
-            lib.dnmf_set_tc_debug(fl)
+            if hasattr(lib, 'dnmf_set_tc_debug'):
+                lib.dnmf_set_tc_debug(fl)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             run(lib, nm, A, W, H, o[nm], *wss[v])
@@ -107,7 +109,8 @@ def main():
             torch.cuda.synchronize()
             if rnd > 0:                      # round 0 = warm-up (attributes, calibration)
                 times[(v, fl, nm)].append(e0.elapsed_time(e1))
-            lib.dnmf_set_tc_debug(0)
+            if hasattr(lib, 'dnmf_set_tc_debug'):
+                lib.dnmf_set_tc_debug(0)
     for v in libs:
         for fl in (flags if v == a.variants.split(',')[0] else [0]):
             rec = {'variant': v, 'dbg': fl}
