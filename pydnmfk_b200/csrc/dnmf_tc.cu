@@ -68,7 +68,8 @@ template <int K, int MODE>
 __global__ void __launch_bounds__(TcCfg<K>::THREADS, 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                float* __restrict__ P, int64_t split_stride, int64_t x_len, int x_blocks, int kt_total,
-               int kt_per_split, int num_units, int hi_mode, int dbg, unsigned long long* __restrict__ prof) {
+               int kt_per_split, int num_units, int hi_mode, int dbg_arg, unsigned long long* __restrict__ prof_arg) {
+  TC_LAB_ARGS(dbg_arg, prof_arg)
   using Cfg = TcCfg<K>;
   constexpr int SA = Cfg::SA, SB = Cfg::SB, NT = Cfg::NT, NBUF = Cfg::NBUF, N2 = Cfg::N2;
   // dbg (DNMF_TC_DBG, timing experiments only, results become wrong): 1 = splitter skips its work, 4 = skip the
@@ -249,15 +250,13 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // every register of the tile has arrived (xor_all reads them all): the smem slot goes back to TMA now
           const uint32_t x = xor_all(raw);
           __syncwarp();
-          if (lane == 0) mbar_arrive(a_free(sa) + (x & ((uint32_t)dbg & 0x40000000u)));
+          if (lane == 0) mbar_arrive(a_free(sa) + (x & ((uint32_t)dbg_arg & 0x40000000u)));
         }
 #endif
         // a - hi(a) is exact; rounding it to tf32 here (nearest) instead of letting the tensor core truncate it
         // removes the one-sided error of the third term
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          lo[j] = tf32_lo_bits(raw[j]);
-        }
+        for (int j = 0; j < 32; j += 2) tf32_lo_bits2(raw[j], raw[j + 1], lo[j], lo[j + 1]);
         TC_T(t_load);
         mbar_wait(t_free(ts), pt ^ 1u);
         TC_T(t_tfree);

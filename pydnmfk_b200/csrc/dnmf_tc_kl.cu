@@ -22,6 +22,11 @@
 // w0 A-TMA | w1 GEMM2 issuer + TMEM owner | w2 Bcat-TMA (lane 0) + Fr-TMA (lane 1) | w3 GEMM1 issuer | w4-7 drain |
 // w8-11, w12-15 [, w16-19] splitter groups.
 #include "generic_passes.cuh"
+// Barrier waits of this file spin on try_wait without the suspend-time hint: measured 2-4 % faster for the KL kernels
+// (the FRO kernels in dnmf_tc.cu keep the hint, which is worth 5 % there) -- tools/kl_lab.py, profiles/r02_kl_lab.md.
+#ifndef DNMF_WAIT_HINT
+#define DNMF_WAIT_HINT 0
+#endif
 #include "tc_common.cuh"
 
 namespace dnmf {
@@ -31,24 +36,35 @@ constexpr int KK = 32;            // factor width handled by this kernel
 // KL_GROUPS splitter groups of 4 warps work on tiles round-robin; the per-tile chain (A tile -> S load -> divide -> split ->
 // tensor-memory store -> GEMM2 -> slot free) is latency-bound, so the number of tiles in flight sets the pass time.
 #ifndef KL_GROUPS
-#define KL_GROUPS 2
+#define KL_GROUPS 3       // round 2: 3 groups are 10-17 % faster than 2 (profiles/r02_kl_lab.md)
 #endif
 constexpr int KL_THREADS = 512 + 128 * (KL_GROUPS - 2);
-// KL_WG_ALIGNED = 1: roles grouped by warpgroup (w0-3 control, w4-7 drain, w8+ splitters), which setmaxnreg needs.
-// KL_WG_ALIGNED = 0: the round-1 placement (w0 A-TMA, w1 GEMM2, w2-5 / w11-14 splitters, w6-9 drain, w10 B/F-TMA, w15 GEMM1):
-// the SM's issue arbiter prefers the higher warp id, so this one lets the GEMM1 issuer and the second splitter group win
-// ties against the first.
-#ifndef KL_WG_ALIGNED
-#define KL_WG_ALIGNED (KL_GROUPS == 3)
+// Warp-role placement.  The SM's issue arbiter prefers the higher warp id, and setmaxnreg moves registers per warpgroup:
+//   KL_PLACE 0  round-1 placement: w0 A-TMA, w1 GEMM2, w2-5 / w11-14 splitters, w6-9 drain, w10 B/F-TMA, w15 GEMM1
+//   KL_PLACE 1  warpgroups, control at the bottom: w0-3 control (A-TMA, GEMM2, B/F-TMA, GEMM1), w4-7 drain, w8+ splitters
+//   KL_PLACE 2  warpgroups, control at the top:    w0.. splitters, then the drain warpgroup, then the control warpgroup
+#ifndef KL_PLACE
+#ifdef KL_WG_ALIGNED
+#define KL_PLACE KL_WG_ALIGNED
+#else
+#define KL_PLACE (KL_GROUPS == 3 ? 2 : 0)
 #endif
-#if KL_GROUPS == 3 && !KL_WG_ALIGNED
-#error "three splitter groups need the warpgroup-aligned role placement"
+#endif
+#if KL_GROUPS == 3 && KL_PLACE == 0
+#error "three splitter groups need a warpgroup-aligned role placement"
 #endif
 constexpr int KL_PAIRS = KL_GROUPS * 128;      // residual pairs per CTA (one per splitter thread)
-constexpr int KL_CHUNK = 4;       // K-tiles accumulated in TMEM before the drain warps fold them into registers
+#ifndef KL_CHUNK_TILES
+#define KL_CHUNK_TILES 4
+#endif
+constexpr int KL_CHUNK = KL_CHUNK_TILES;       // K-tiles accumulated in TMEM before the drain warps fold them into registers
 
+// KL_PACKED = 1: the splitters' fp32 arithmetic uses the packed two-element instructions (FADD2 / FMUL2).
 // KL_S1 = 1: GEMM1 adds its three split terms into ONE 32-column accumulator (umma_tile_cat); the splitters then load
 // 32 S columns per row instead of 64 and skip an addition, and the freed tensor-memory columns deepen the rings.
+#ifndef KL_PACKED
+#define KL_PACKED 1
+#endif
 #ifndef KL_S1
 #define KL_S1 0       // measured slower on B200 (12 N=32 MMAs cost more tensor-pipe time than 4 x {N=64, N=32})
 #endif
@@ -85,6 +101,11 @@ struct KlCfg {
   static constexpr int S_COL0 = OP_COL0 + NT * 64;
   static constexpr int FX_COL0 = S_COL0 + NS * S_COLS; // 448
   static_assert(FX_COL0 + 64 <= 512, "TMEM has 512 columns");
+  // A splitter group waits on a ring slot by phase PARITY, which is only unambiguous while the slot's previous use has
+  // completed.  The group knows that for every tile up to its own previous one (tile - KL_GROUPS; GEMM1 and GEMM2 complete
+  // in tile order), and the slot's previous use is tile - NS (resp. tile - NT): both rings need at least KL_GROUPS slots,
+  // otherwise a group that runs ahead passes the wait one phase early (observed as a hang with NS = 2 and 3 groups).
+  static_assert(NS >= KL_GROUPS && NT >= KL_GROUPS, "S and operand rings need one slot per splitter group");
   static constexpr int NBARS = 2 * SA + 2 * SB + 2 * SF + 2 * NT + 2 * NS + 2 * NBUF + 2;
   static constexpr int BAR_BYTES = 1024;
   static_assert((NBARS + 1) * 8 <= BAR_BYTES, "barrier area too small");
@@ -99,8 +120,9 @@ __global__ void __launch_bounds__(KL_THREADS, 1)
 tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmF, const float* __restrict__ Fx, int64_t ldfx, int64_t fr_rows_pad,
              float* __restrict__ P, int64_t split_stride, int64_t x_len, int x_blocks, int kt_total, int kt_per_split,
-             int num_units, int k_real, float eps, int dbg, double* __restrict__ pairs_out,
-             unsigned long long* __restrict__ prof) {
+             int num_units, int k_real, float eps, int dbg_arg, double* __restrict__ pairs_out,
+             unsigned long long* __restrict__ prof_arg) {
+  TC_LAB_ARGS(dbg_arg, prof_arg)
   // dbg (dnmf_set_tc_debug, timing ablations only -- results become wrong): 1 skip the division, 2 skip the S load,
   // 4 skip the GEMM1 MMAs, 8 skip the GEMM2 low-order MMAs, 16 skip all GEMM2 MMAs, 32 skip the U split, 64 skip the
   // shared-memory read of the A tile, 0x10000 skip the Bcat TMA loads, 0x20000 skip the FrCat TMA loads
@@ -141,7 +163,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_init(bar(iXE), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(bar(iSLOT), 512);
+  if (warp == 1) tmem_alloc(bar(iSLOT), 512);      // (allocation and release by the same warp; any role)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -151,12 +173,17 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // warpgroup needs far fewer and hands the rest to the splitter warpgroups (setmaxnreg works per warpgroup, hence the
   // warpgroup-aligned roles).  setmaxnreg.inc can only draw on what the CTA's own warpgroups released (the CTA's pool is
   // its launch allocation, 640 x 96): 4 x 32 + 4 x 80 + 12 x 120 registers x 32 lanes = 60416 <= 61440.
-#if KL_WG_ALIGNED
-  constexpr int W_BPROD = 2, W_G1 = 3;
+#if KL_PLACE == 1
+  constexpr int W_APROD = 0, W_G2 = 1, W_BPROD = 2, W_G1 = 3;
   const bool is_ctrl = warp < 4, is_split = warp >= 8;
   const int split_group = (warp - 8) >> 2, first_split_warp = 8;
+#elif KL_PLACE == 2
+  constexpr int W_CTRL0 = 4 * KL_GROUPS + 4;
+  constexpr int W_APROD = W_CTRL0, W_BPROD = W_CTRL0 + 1, W_G2 = W_CTRL0 + 2, W_G1 = W_CTRL0 + 3;
+  const bool is_ctrl = warp >= W_CTRL0, is_split = warp < 4 * KL_GROUPS;
+  const int split_group = warp >> 2, first_split_warp = 0;
 #else
-  constexpr int W_BPROD = 10, W_G1 = 15;
+  constexpr int W_APROD = 0, W_G2 = 1, W_BPROD = 10, W_G1 = 15;
   const bool is_ctrl = warp < 2 || warp == W_BPROD || warp == W_G1;
   const bool is_split = (warp >= 2 && warp < 6) || (warp >= 11 && warp < 15);
   const int split_group = warp >= 11 ? 1 : 0, first_split_warp = 2;
@@ -165,7 +192,8 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #if KL_GROUPS == 3
   asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
 #endif
-  if (warp == 0) {
+  (void)W_G2;
+  if (warp == W_APROD) {
     // ===================== A producer =====================
     if (lane == 0) {
       int s = 0;
@@ -373,7 +401,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // every register of the tile has arrived (xor_all reads them all): the smem slot goes back to TMA now
           const uint32_t x = xor_all(u);
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(iAE + sa) + (x & ((uint32_t)dbg & 0x40000000u)));
+          if (lane == 0) mbar_arrive(bar(iAE + sa) + (x & ((uint32_t)dbg_arg & 0x40000000u)));
         }
 #endif
         // S tile of this accumulator row
@@ -431,6 +459,20 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             continue;
           }
+#if KL_PACKED && !KL_S1
+          // two elements per FADD2 / FMUL2 (sm_100 packed fp32): the same roundings as the scalar code below, half the
+          // FMA-pipe instructions of the warps whose instruction stream sets the pass time
+#pragma unroll
+          for (int j = 0; MODE != 3 && j < 32; j += 2) {
+            float2 den = __fadd2_rn(make_float2(__uint_as_float(s0[j]), __uint_as_float(s0[j + 1])),
+                                    make_float2(__uint_as_float(s1[j]), __uint_as_float(s1[j + 1])));
+            den = __fadd2_rn(den, make_float2(eps, eps));
+            const float2 q2 = (dbg & 1) ? den : make_float2(rcp_approx(den.x), rcp_approx(den.y));
+            const float2 uu = __fmul2_rn(make_float2(__uint_as_float(u[j]), __uint_as_float(u[j + 1])), q2);
+            u[j] = __float_as_uint(uu.x);
+            u[j + 1] = __float_as_uint(uu.y);
+          }
+#else
 #pragma unroll
           for (int j = 0; MODE != 3 && j < 32; ++j) {
             const float den = KL_S_OF(j) + eps;
@@ -439,15 +481,24 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             // rounding errors of the 65536 quotients of a row are independent and average out in the contraction.
             u[j] = __float_as_uint((dbg & 1) ? a * den : a * rcp_approx(den));
           }
+#endif
 #undef KL_S_OF
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iSE + ss));          // S slot may be overwritten
+#if KL_PACKED
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          if (dbg & 32) { lo[j] = u[j]; lo[j + 1] = u[j + 1]; continue; }
+          tf32_lo_bits2(u[j], u[j + 1], lo[j], lo[j + 1]);
+        }
+#else
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           lo[j] = (dbg & 32) ? u[j] : tf32_lo_bits(u[j]);
         }
+#endif
         TC_T(t_div);
         mbar_wait(bar(iTE + ts), pt ^ 1u);
         TC_T(t_tfree);

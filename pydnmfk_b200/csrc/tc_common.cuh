@@ -380,8 +380,34 @@ __device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t raw) {
   const float v = __uint_as_float(raw);
   return __float_as_uint(v - __uint_as_float(raw & 0xFFFFE000u)) + 0x1000u;
 }
+// the same for two elements with one packed subtraction (FADD2, sm_100): one LOP3 per element forms -trunc_tf32(a), one
+// FADD2 per pair adds it (exact), one integer add per element applies the half-ulp bias
+__device__ __forceinline__ void tf32_lo_bits2(uint32_t raw0, uint32_t raw1, uint32_t& lo0, uint32_t& lo1) {
+  const float2 nh = make_float2(__uint_as_float((raw0 & 0xFFFFE000u) ^ 0x80000000u),
+                                __uint_as_float((raw1 & 0xFFFFE000u) ^ 0x80000000u));
+  const float2 l = __fadd2_rn(make_float2(__uint_as_float(raw0), __uint_as_float(raw1)), nh);
+  lo0 = __float_as_uint(l.x) + 0x1000u;
+  lo1 = __float_as_uint(l.y) + 0x1000u;
+}
 
 
+// DNMF_TC_LAB = 1 (tools/build_variant.sh, tools/kl_lab.py, tools/prof_tc.py --roles): the kernels honour the
+// timing-ablation word (dnmf_set_tc_debug) and the per-role cycle counters (dnmf_set_tc_profile).  The production build
+// (0) compiles both out: the flag tests, the register copies that join their alternative code paths and the predicated
+// clock reads cost the splitter warps ~15 % of their issue slots (round-2 ncu source page).
+#ifndef DNMF_TC_LAB
+#define DNMF_TC_LAB 0
+#endif
+#if DNMF_TC_LAB
+#define TC_LAB_ARGS(dbg_arg, prof_arg) const int dbg = (dbg_arg); unsigned long long* const prof = (prof_arg);
+#else
+// DNMF_TC_DBG_CONST: ablation word fixed at compile time (lab builds that remove one stage without paying for the
+// run-time flag tests); 0 in production
+#ifndef DNMF_TC_DBG_CONST
+#define DNMF_TC_DBG_CONST 0
+#endif
+#define TC_LAB_ARGS(dbg_arg, prof_arg) constexpr int dbg = DNMF_TC_DBG_CONST; constexpr unsigned long long* prof = nullptr; (void)(dbg_arg); (void)(prof_arg);
+#endif
 // cycle accounting (dnmf_set_tc_profile): per-role time split written to a debug buffer; off in production
 #define TC_T(var) do { if (prof) { const long long _n = clock64(); var += _n - tprev; tprev = _n; } } while (0)
 

@@ -3,8 +3,9 @@
     python tools/kl_lab.py --variants default,late --dbg 0,1,65536 [--m 65536 --n 65536 --k 32] [--rounds 6]
 
 Every library variant (pydnmfk_b200/libdnmf_<name>.so from tools/build_variant.sh; "default" = libdnmf.so) is loaded
-side by side with ctypes and the (variant, flag set, op) combinations are timed ROUND-ROBIN for `--rounds` rounds, so
-that clock / power drift of the box hits all of them alike; the report is the median and minimum per combination.
+side by side with ctypes and the (variant, flag set, op) combinations are timed in a reshuffled order for `--rounds`
+rounds, each paired with a reference launch issued right before it (see below); the report is the median ratio to the
+reference plus the median and minimum time per combination.
 Flag sets are the timing-ablation bits of dnmf_set_tc_debug (non-zero values give wrong results; they only locate the
 bottleneck).  For flags 0 every variant is also checked against float64 numpy on a 2048 x 1536 shard."""
 import argparse
@@ -27,6 +28,7 @@ def main():
     ap.add_argument('--n', type=int, default=65536)
     ap.add_argument('--k', type=int, default=32)
     ap.add_argument('--rounds', type=int, default=6)
+    ap.add_argument('--sustained', type=int, default=0, help='also time blocks of N back-to-back (op, op, ...) sequences per variant: the power-capped steady state of the product loop')
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -95,29 +97,75 @@ def main():
     gb = a.m * a.n * 4 / 1e9
     wss = {v: workspace(lib, a.m, a.n) for v, lib in libs.items()}
     flags = [int(x, 0) for x in a.dbg.split(',')]
-    combos = [(v, fl, nm) for v in libs for fl in (flags if v == a.variants.split(',')[0] else [0]) for nm in names]
+    first = a.variants.split(',')[0]
+    combos = [(v, fl, nm) for v in libs for fl in (flags if v == first else [0]) for nm in names]
+    # Every measurement is PAIRED with a reference launch (the first variant's FRO pass `ah`, flags 0) issued right
+    # before it on the same stream with no host synchronisation in between: the whole round is one back-to-back queue
+    # (sustained clocks, like the product's loop), the order of the combinations is reshuffled every round, and the
+    # report is the median of the per-pair ratio t / t_ref next to the absolute times -- box drift cancels in the ratio.
+    import random
+    rng = random.Random(1)
     times = {c: [] for c in combos}
+    ratios = {c: [] for c in combos}
+    ref_times = []
     for rnd in range(a.rounds + 1):
-        for (v, fl, nm) in combos:
+        order = combos[:]
+        rng.shuffle(order)
+        evs = []
+        for (v, fl, nm) in order:
             lib = libs[v]
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            if hasattr(libs[first], 'dnmf_set_tc_debug'):
+                libs[first].dnmf_set_tc_debug(0)
+            e0.record()
+            run(libs[first], 'ah', A, W, H, o['ah'], *wss[first])
+            e1.record()
             if hasattr(lib, 'dnmf_set_tc_debug'):
                 lib.dnmf_set_tc_debug(fl)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
             run(lib, nm, A, W, H, o[nm], *wss[v])
-            e1.record()
-            torch.cuda.synchronize()
-            if rnd > 0:                      # round 0 = warm-up (attributes, calibration)
-                times[(v, fl, nm)].append(e0.elapsed_time(e1))
+            e2.record()
             if hasattr(lib, 'dnmf_set_tc_debug'):
                 lib.dnmf_set_tc_debug(0)
+            evs.append(((v, fl, nm), e0, e1, e2))
+        torch.cuda.synchronize()
+        if rnd > 0:                          # round 0 = warm-up (attributes, calibration)
+            for c, e0, e1, e2 in evs:
+                tr, t = e0.elapsed_time(e1), e1.elapsed_time(e2)
+                ref_times.append(tr)
+                times[c].append(t)
+                ratios[c].append(t / tr)
+    print(json.dumps({'reference': first + ':ah', 'median_ms': statistics.median(ref_times), 'min_ms': min(ref_times),
+                      'max_ms': max(ref_times)}), flush=True)
     for v in libs:
-        for fl in (flags if v == a.variants.split(',')[0] else [0]):
+        for fl in (flags if v == first else [0]):
             rec = {'variant': v, 'dbg': fl}
             for nm in names:
                 t = times[(v, fl, nm)]
-                rec[nm] = {'median_ms': statistics.median(t), 'min_ms': min(t), 'GBps_median': gb / statistics.median(t) * 1e3}
+                rec[nm] = {'median_ms': statistics.median(t), 'min_ms': min(t), 'ratio_to_ref_median': statistics.median(ratios[(v, fl, nm)]),
+                           'GBps_median': gb / statistics.median(t) * 1e3}
             print(json.dumps(rec), flush=True)
+
+    if a.sustained:
+        # Sustained blocks: `--sustained` back-to-back repetitions of the op list per variant with no host sync (what a
+        # CUDA-graph replayed fit does to the power budget), variants in a reshuffled order every round.
+        blocks = {v: [] for v in libs}
+        for rnd in range(a.rounds + 1):
+            order = list(libs)
+            rng.shuffle(order)
+            for v in order:
+                lib = libs[v]
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(a.sustained):
+                    for nm in names:
+                        run(lib, nm, A, W, H, o[nm], *wss[v])
+                e1.record()
+                torch.cuda.synchronize()
+                if rnd > 0:
+                    blocks[v].append(e0.elapsed_time(e1) / (a.sustained * len(names)))
+        for v in libs:
+            print(json.dumps({'variant': v, 'sustained_ms_per_pass_median': statistics.median(blocks[v]),
+                              'min': min(blocks[v]), 'max': max(blocks[v]), 'ops': names, 'reps': a.sustained}), flush=True)
 
 
 if __name__ == '__main__':
