@@ -1,7 +1,7 @@
 """Golden vectors for the NMFk-level rows (clustering, silhouettes, nnsvd, rank selection, NMFk end to end),
 produced by the UNMODIFIED reference on forked ranks.  TEST INFRASTRUCTURE; authoring container only.
 
-    python oracle/gen_golden_nmfk.py [cluster] [nnsvd] [nnsvdfit] [pvalue] [e2e]
+    python oracle/gen_golden_nmfk.py [cluster] [nnsvd] [nnsvdfit] [pvalue] [e2e] [cfg5]
 
 Writes tests/golden/nmfk_cases.npz, copies the reference's own small fixtures for this path (tests/sill.npy,
 tests/nnsvd_factors_*.npy -> tests/golden/ref_*.npy/.npz) and the example matrices (data/wtsi.mat -> wtsi_X.npy, 96 x 21;
@@ -187,6 +187,19 @@ def main(argv):
                 res = run_ranks(case['grid'][0] * case['grid'][1], _ref_e2e, (case, tmp), timeout=3000)
             put('e2e/' + case['name'], res)
             print('e2e %-20s nopt=%d' % (case['name'], res[0]['nopt']), flush=True)
+    if 'cfg5' in argv:
+        case = K.CFG5_CASE
+        with tempfile.TemporaryDirectory() as tmp:
+            res = run_ranks(case['grid'][0] * case['grid'][1], _ref_e2e, (case, tmp), timeout=6000)
+        out = {}
+        for r, o in enumerate(res):
+            for key, val in o.items():
+                out['e2e/%s/%d/%s' % (case['name'], r, key)] = val
+        p5 = os.path.join(K.GOLDEN, 'nmfk_cfg5.npz')
+        np.savez_compressed(p5, **out)
+        print('cfg5 %-20s nopt=%d' % (case['name'], res[0]['nopt']), 'wrote', p5, os.path.getsize(p5), 'bytes', flush=True)
+        if what == {'cfg5'}:
+            return
     np.savez_compressed(path, **store)
     print('wrote', path, os.path.getsize(path), 'bytes')
 

@@ -135,6 +135,13 @@ E2E_CASES = [
 ]
 E2E_BY_NAME = {c['name']: c for c in E2E_CASES}
 
+# BASELINE.json configs[4] exactly as stated (examples/dist_pynmfk_1d_wtsi.py:26-44 expects nopt == 4): nnsvd init on the
+# 2 x 1 grid it requires, k = 2..10, 20 perturbations, KL-MU, 1000 iterations.  ~5 min through the unmodified reference,
+# so it has its own golden file (tests/golden/nmfk_cfg5.npz, `python oracle/gen_golden_nmfk.py cfg5`) and is checked by
+# tools/bench_cfg5.py on the GPUs rather than by every test run.
+CFG5_CASE = dict(name='wtsi_2x1_nnsvd_cfg5', grid=(2, 1), init='nnsvd', start_k=2, end_k=10, perturbations=20, itr=1000,
+                 noise_var=0.015, sill_thr=0.9, norm='kl', method='mu')
+
 
 def wtsi():
     """The 96 x 21 mutation-count matrix of the reference's NMFk example (data/wtsi.mat, key 'X'), stored as a fixture."""
