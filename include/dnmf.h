@@ -154,6 +154,20 @@ int dnmf_sqnorm(const void* X, int64_t ldx, int64_t rows, int64_t cols, double* 
 int dnmf_normalize(void* W, int64_t ldw, int64_t m, void* H, int64_t ldh, int64_t n, int64_t k,
                    const void* s, double eps, int dtype, void* stream);
 
+/* The two factor-sized inner products of the trace identity
+ *     ||A - W H||_F^2 = ||A||_F^2 - 2 <W, A H^T> + <W^T W, H H^T>
+ * (the per-iteration error monitor; the returned recon_err stays the direct residual):
+ *   out[2 s]     = sum_ij W[i][j] V[i][j]     W, V = A H^T: this rank's [m x k] rows (sum over ranks by the caller)
+ *   out[2 s + 1] = sum_ij G1[i][j] G2[i][j]   G1 = W^T W, G2 = H H^T: the global [k x k] Grams
+ * as float64, two-stage fixed-order reductions.  s = 0, or -- with `slot_counter` -- the int64 read from device memory,
+ * which the call then advances (samples beyond max_slots are dropped): a CUDA-graph replay of the step appends to a
+ * history.  Replaces the A-sized temporary A - W_i @ H_j of pyDNMF.py:208-209 for monitoring; the operands are what
+ * dist_nmf.py:729-732 / :242-245 has at hand anyway (H H^T, A H^T) plus the W^T W of the preceding H half-step (:748). */
+int64_t dnmf_trace_terms_workspace_bytes(void);
+int dnmf_trace_terms(const void* W, int64_t ldw, const void* V, int64_t ldv, int64_t m,
+                     const void* G1, const void* G2, int64_t k, double* out, int64_t* slot_counter,
+                     int64_t max_slots, int dtype, void* ws, int64_t ws_bytes, void* stream);
+
 /* out[0] = ||A - W H||_F^2, out[1] = ||A||_F^2 (float64), one pass over A, no m x n temporary
  *   replaces pyDNMF.py:208-209,215 and dist_nmf.py:556,:1024 */
 int dnmf_residual_sqnorm(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh,

@@ -356,6 +356,37 @@ int dnmf_sqnorm(const void* X, int64_t ldx, int64_t rows, int64_t cols, double* 
   return 0;
 }
 
+int64_t dnmf_trace_terms_workspace_bytes(void) { return (int64_t)(2 * 1024) * (int64_t)sizeof(double); }
+
+int dnmf_trace_terms(const void* W, int64_t ldw, const void* V, int64_t ldv, int64_t m, const void* G1, const void* G2,
+                     int64_t k, double* out, int64_t* slot_counter, int64_t max_slots, int dtype, void* ws, int64_t ws_bytes,
+                     void* stream) {
+  if (int rc = check_common(m, 0, k, dtype)) return rc;
+  DNMF_CHECK_ARG(W && V && G1 && G2 && out, "null pointer");
+  DNMF_CHECK_ARG(slot_counter == nullptr || max_slots >= 1, "max_slots must be >= 1 with a slot counter");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ws == nullptr || ws_bytes < dnmf_trace_terms_workspace_bytes())
+    return fail(DNMF_E_WORKSPACE, "trace_terms needs %lld workspace bytes, got %lld", (long long)dnmf_trace_terms_workspace_bytes(), (long long)ws_bytes);
+  double* P = (double*)ws;
+  // <W, V>: at most 1024 blocks of whole 2048-element spans; <G1, G2>: k*k <= 4096 elements, at most 2 blocks
+  const int64_t tot0 = m * k, tot1 = k * k;
+  const int64_t per0 = round_up(ceil_div(tot0 > 0 ? tot0 : 1, (int64_t)1024), (int64_t)2048);
+  const int64_t n0 = tot0 > 0 ? ceil_div(tot0, per0) : 0;
+  const int64_t per1 = 2048;
+  const int64_t n1 = tot1 > 0 ? ceil_div(tot1, per1) : 0;
+  if (n0 > 0) {
+    DISPATCH_T(dtype, (dot_partial_kernel<T><<<(unsigned)n0, 256, 0, st>>>((const T*)W, ldw, (const T*)V, ldv, m, (int)k, per0, P)));
+    DNMF_LAUNCH_CHECK("dot_partial_kernel<W,V>");
+  }
+  if (n1 > 0) {
+    DISPATCH_T(dtype, (dot_partial_kernel<T><<<(unsigned)n1, 256, 0, st>>>((const T*)G1, k, (const T*)G2, k, k, (int)k, per1, P + n0)));
+    DNMF_LAUNCH_CHECK("dot_partial_kernel<G,G>");
+  }
+  trace_store_kernel<<<1, 256, 0, st>>>(P, n0, n1, out, slot_counter, max_slots);
+  DNMF_LAUNCH_CHECK("trace_store_kernel");
+  return 0;
+}
+
 int dnmf_normalize(void* W, int64_t ldw, int64_t m, void* H, int64_t ldh, int64_t n, int64_t k, const void* s,
                    double eps, int dtype, void* stream) {
   if (int rc = check_common(m, n, k, dtype)) return rc;

@@ -17,7 +17,7 @@
 //     are summed in a fixed order by reduce_partials_kernel (deterministic).
 //
 // Warp roles (one persistent CTA per SM):  w0 A-TMA | w1 MMA issuer + TMEM owner | w2-5 splitters | w6-9 drain |
-// w10 B-TMA | w11-14 second splitter group (k <= 32).
+// w10 B-TMA | w11-14 second splitter group | w15-18 second drain set (k = 64: columns 32-63).
 #include "generic_passes.cuh"
 #include "tc_api.cuh"
 #include "tc_common.cuh"
@@ -42,10 +42,13 @@ struct TcCfg {
   static constexpr int SA = (K == 16) ? 10 : (K == 32) ? 8 : 7;
   static constexpr int SB = (K == 16) ? 12 : (K == 32) ? 10 : 6;
   static constexpr int NBUF = (K == 16) ? 4 : (K == 32) ? 3 : 2;
-  // splitter groups working on alternate tiles (hides the tcgen05.st round trip); the K=64 drain warps need too many
-  // registers for 480 threads per CTA, so that variant keeps one group
-  static constexpr int SG = (K <= 32) ? 2 : 1;
-  static constexpr int THREADS = TC_THREADS_BASE + 128 * (SG - 1);
+  // two splitter groups work on alternate tiles (hides the tcgen05.st round trip).  The K = 64 drain needs 64 accumulator
+  // registers per thread on top of the load buffers -- too many for the 600-thread CTA that two groups make -- so there
+  // TWO drain warps share each tensor-memory lane quarter, each folding 32 of the 64 output columns (DW = 2).
+  static constexpr int SG = 2;
+  static constexpr int DW = (K <= 32) ? 1 : 2;
+  static constexpr int KD = K / DW;                   // output columns per drain warp
+  static constexpr int THREADS = TC_THREADS_BASE + 128 * (SG - 1) + 128 * (DW - 1);
   static constexpr int OP_COL0 = NBUF * N2;
   static constexpr int NT = (512 - OP_COL0) / 64;
   static constexpr int TMEM_COLS = 512;
@@ -102,7 +105,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_free(s), 4); }
     for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_free(s), 1); }
     for (int s = 0; s < NT; ++s) { mbar_init(t_full(s), 4); mbar_init(t_free(s), 1); }
-    for (int b = 0; b < NBUF; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4 * Cfg::DW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -207,7 +210,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prof[blockIdx.x * 16 + 5] = t_mma; prof[blockIdx.x * 16 + 6] = t_commit;
       }
     }
-  } else if (warp < 6 || warp >= 11) {
+  } else if (warp < 6 || (warp >= 11 && warp < 15)) {
     // ===================== splitters (warps 2-5 [+ 11-14]): smem A tile -> registers -> {A, A - hi(A)} in TMEM =====
     // Thread (q, lane) owns accumulator row q*32+lane: a row of A (AH) or a column of A (WTA).  With two groups,
     // group g takes the tiles whose running index is congruent to g (mod 2).
@@ -293,6 +296,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The tensor core adds into its fp32 accumulator with truncation; draining every TC_CHUNK K-tiles and summing the
     // chunks here with round-to-nearest keeps that bias at the level of plain fp32 arithmetic.
     const int q = warp & 3;               // TMEM lane quarter this warp may access
+    constexpr int KD = Cfg::KD;
+    const int c0 = (Cfg::DW == 2 && warp >= 15) ? KD : 0;     // first output column of this drain warp
     int buf = 0;
     uint32_t accphase = 0;
     constexpr int CH = 16;
@@ -302,17 +307,17 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kt0 = sp * kt_per_split;
       const int kt1 = min(kt_total, kt0 + kt_per_split);
       const int nchunks = (kt1 - kt0 + TC_CHUNK - 1) / TC_CHUNK;
-      float acc[K];
+      float acc[KD];
 #pragma unroll
-      for (int j = 0; j < K; ++j) acc[j] = 0.f;
+      for (int j = 0; j < KD; ++j) acc[j] = 0.f;
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(accf_bar(buf), accphase);
         TC_T(t_accf);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N2);
-        constexpr int HALF = (K >= 32) ? 32 : K;       // columns folded per batch of loads
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N2 + c0);
+        constexpr int HALF = (Cfg::DW == 2) ? 16 : ((KD >= 32) ? 32 : KD);       // columns folded per batch of loads
 #pragma unroll
-        for (int h0 = 0; h0 < K; h0 += HALF) {
+        for (int h0 = 0; h0 < KD; h0 += HALF) {
           uint32_t a[HALF], b[HALF];
 #pragma unroll
           for (int j0 = 0; j0 < HALF; j0 += CH) {
@@ -331,9 +336,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int64_t x = (int64_t)xb * TC_BM + q * 32 + lane;
       if (x < x_len) {
-        float* orow = P + (int64_t)sp * split_stride + x * K;
+        float* orow = P + (int64_t)sp * split_stride + x * K + c0;
 #pragma unroll
-        for (int j = 0; j < K; j += 4)
+        for (int j = 0; j < KD; j += 4)
           *reinterpret_cast<float4*>(orow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
     }

@@ -278,6 +278,49 @@ rowsum_partial_kernel(const T* __restrict__ X, int64_t ldx, int64_t rows, int64_
   if (threadIdx.x == 0) P[(int64_t)blockIdx.y * rows + r] = s;
 }
 
+// inner product of two [rows x cols] matrices, stage 1: block b sums the flat elements [b * per_block, (b + 1) * per_block)
+// in a fixed order into P[b] (float64)
+template <typename T>
+__global__ void __launch_bounds__(256)
+dot_partial_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ Y, int64_t ldy, int64_t rows, int cols,
+                   int64_t per_block, double* __restrict__ P) {
+  __shared__ double red[8];
+  const int64_t total = rows * cols;
+  const int64_t begin = (int64_t)blockIdx.x * per_block;
+  const int64_t end = (begin + per_block < total) ? (begin + per_block) : total;
+  double acc = 0.0;
+  for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    acc += (double)X[r * ldx + c] * (double)Y[r * ldy + c];
+  }
+  const double s = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) P[blockIdx.x] = s;
+}
+
+// stage 2 of dnmf_trace_terms: out[2 * slot] = sum P[0, n0), out[2 * slot + 1] = sum P[n0, n0 + n1), slot read from (and
+// then advanced in) device memory so that a CUDA-graph replay of the step appends to a history instead of overwriting it
+static __global__ void __launch_bounds__(256) trace_store_kernel(const double* __restrict__ P, int64_t n0, int64_t n1,
+                                                                 double* __restrict__ out, int64_t* __restrict__ slot_counter,
+                                                                 int64_t max_slots) {
+  __shared__ double red[8];
+  double a0 = 0.0, a1 = 0.0;
+  for (int64_t i = threadIdx.x; i < n0; i += 256) a0 += P[i];
+  for (int64_t i = threadIdx.x; i < n1; i += 256) a1 += P[n0 + i];
+  const double s0 = block_sum<256>(a0, red);
+  const double s1 = block_sum<256>(a1, red);
+  if (threadIdx.x == 0) {
+    int64_t slot = 0;
+    if (slot_counter != nullptr) {
+      slot = *slot_counter;
+      *slot_counter = slot + 1;
+      if (slot >= max_slots) return;          // history full: keep counting, drop the sample
+    }
+    out[2 * slot] = s0;
+    out[2 * slot + 1] = s1;
+  }
+}
+
 // final scalar: out[0] = sum_i P[i]  (single block, fixed order)
 static __global__ void __launch_bounds__(256) sum_all_kernel(const double* __restrict__ P, int64_t count, double* out) {
   __shared__ double red[8];

@@ -242,6 +242,20 @@ class DeviceOps:
         L.call('dnmf_normalize', W.data_ptr(), _ld(W), m, H.data_ptr(), _ld(H), n, k, s.data_ptr(), float(eps),
                _DT[W.dtype], self._stream())
 
+    def trace_terms(self, W, V, G1, G2, out=None, slot_counter=None):
+        """[<W, V>, <G1, G2>] as float64 (include/dnmf.h: dnmf_trace_terms).  With ``out`` [slots, 2] and an int64
+        ``slot_counter`` device tensor the pair is appended at the counter's position (graph-replay safe)."""
+        m, k = W.shape
+        dt = _DT[W.dtype]
+        if out is None:
+            out = self.empty((1, 2), torch.float64)
+        wsb = int(L.call('dnmf_trace_terms_workspace_bytes'))
+        ws = self.workspace(wsb)
+        L.call('dnmf_trace_terms', W.data_ptr(), _ld(W), V.data_ptr(), _ld(V), m, G1.data_ptr(), G2.data_ptr(), k,
+               out.data_ptr(), slot_counter.data_ptr() if slot_counter is not None else None, out.shape[0], dt,
+               ws, wsb, self._stream())
+        return out
+
     def residual_sqnorm(self, A, W, H):
         """[||A - W H||_F^2, ||A||_F^2] as a float64 device tensor of shape [2]."""
         m, n = A.shape

@@ -75,6 +75,55 @@ class _AlgBase:
         else:
             raise Exception('Not a valid norm: Choose (fro/kl)')
 
+    # ---- per-iteration error monitor (trace identity) ---------------------------------------------------
+    # ||A - W H||^2 = ||A||^2 - 2 <W, A H^T> + <W^T W, H H^T>.  At the top of a FRO-MU W half-step H H^T and A H^T of the
+    # current H are at hand and W^T W of the current W was formed by the preceding H half-step: the error of the state the
+    # previous iteration left costs two factor-sized inner products (dnmf_trace_terms), no pass over A.  Samples are
+    # appended to a device history through a device-side counter, so CUDA-graph replays of the step keep recording.
+    def _monitor_setup(self):
+        self._mon = None
+        if not getattr(self.params, 'err_monitor', False) or self.norm.upper() != 'FRO' or self.method.upper() != 'MU':
+            return
+        slots = int(getattr(self.params, 'itr', 1)) + 1
+        dev = self.A_ij.device
+        m = type('Monitor', (), {})()
+        m.hist = torch.zeros((slots, 2), dtype=torch.float64, device=dev)
+        m.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        m.wtw = torch.zeros((self.k, self.k), dtype=self.A_ij.dtype, device=dev)   # persistent: captured graphs keep its address
+        m.have_wtw = False
+        m.anorm2 = self._sqnorm_dev(self.A_ij)            # global ||A||^2, float64 device scalar
+        m.w_sharded = (self.p > 1) and not (self.p_r == 1)   # <W, A H^T> is a sum over the ranks that own W rows
+        self._mon = m
+        self.params.err_monitor_state = m
+
+    def _monitor_sample(self, W, AH, HHT):
+        m = self._mon
+        if m is None or not m.have_wtw or self.W_update != True:  # noqa: E712  (no W^T W of the current W yet)
+            return
+        # every rank appends ITS pair (graph-replay safe); on grids that shard W the histories are summed once at the end
+        self.ops.trace_terms(W, AH, m.wtw, HHT, out=m.hist, slot_counter=m.counter)
+
+    def _monitor_keep(self, W_TW):
+        if self._mon is not None:
+            self._mon.wtw.copy_(W_TW)
+            self._mon.have_wtw = True
+
+    def monitor_history(self):
+        """Relative errors ||A - W H||_F / ||A||_F recorded so far (numpy float64): entry i is the state at the top of
+        iteration i + 1, i.e. the result of iteration i."""
+        m = getattr(self, '_mon', None)
+        if m is None:
+            return None
+        n = min(int(m.counter.item()), m.hist.shape[0])
+        hist = m.hist
+        if m.w_sharded:
+            # <W, A H^T> is a sum over the ranks that own W rows; <W^T W, H H^T> is global on every rank already
+            hist = self.comm1.allreduce_(m.hist.clone())
+            hist[:, 1] /= float(self.comm1.size)
+        h = hist[:n].cpu().numpy()
+        a2 = float(m.anorm2.item())
+        return np.sqrt(np.maximum(a2 - 2.0 * h[:, 0] + h[:, 1], 0.0) / a2)
+
     # ---- BCD shared by both grids (dist_nmf.py:503-579, :971-1047) ---------------------------------
     # The Lipschitz bounds, objective, momentum weights and the accept / restore decision live in a float64 device
     # vector (csrc/dnmf_bcd.cu): one iteration is a fixed sequence of launches with no host round trip, replayed as a
@@ -156,6 +205,7 @@ class nmf_algorithms_2D(_AlgBase):
         self._h_sizes = [int(s) for s in self.cartesian1d_row.allgather(int(self.local_H_n))]
         self.W_i = None
         self.H_j = None
+        self._monitor_setup()
 
     def _W(self):
         return self.W_ij
@@ -243,6 +293,7 @@ class nmf_algorithms_2D(_AlgBase):
     def Fro_MU_update_H(self):
         """dist_nmf.py:207-225."""
         W_TW = self._gram_W(self.W_ij)
+        self._monitor_keep(W_TW)
         Yt, _ = self._WTA(self.W_ij)
         self.ops.mu_update_h(self.H_ij, Yt, W_TW, self.eps, y_transposed=True)
 
@@ -250,6 +301,7 @@ class nmf_algorithms_2D(_AlgBase):
         """dist_nmf.py:227-245."""
         HH_T = self._gram_H(self.H_ij)
         AH = self._AH(self.H_ij)
+        self._monitor_sample(self.W_ij, AH, HH_T)
         self.ops.mu_update_w(self.W_ij, AH, HH_T, self.eps)
 
     def Fro_MU_update(self, W_update=True):
@@ -350,6 +402,9 @@ class nmf_algorithms_1D(_AlgBase):
         self._px = None
         if self.p_c == 1 and self.p_r > 1 and self.comm1.size == self.p_r and self.H_j.stride(1) == 1:
             self._px = peer.get(self.comm1, self.H_j.shape[1], self.k, self.H_j.dtype)
+        self._monitor_setup()
+        if self._mon is not None:
+            self._px = None          # the monitor needs the global W^T W, which the peer exchange never materialises
 
     def _W(self):
         return self.W_i
@@ -404,6 +459,7 @@ class nmf_algorithms_1D(_AlgBase):
         """dist_nmf.py:715-732."""
         HH_T = self._gram_H(self.H_j)
         AH = self._AH(self.H_j)
+        self._monitor_sample(self.W_i, AH, HH_T)
         self.ops.mu_update_w(self.W_i, AH, HH_T, self.eps)
 
     @comm_timing()
@@ -415,6 +471,7 @@ class nmf_algorithms_1D(_AlgBase):
             self._px.update_h(0, self.H_j, Yt, G, self.eps)
             return
         W_TW = self._gram_W(self.W_i)
+        self._monitor_keep(W_TW)
         AtW, _ = self._WTA(self.W_i)
         self.ops.mu_update_h(self.H_j, AtW, W_TW, self.eps)
 

@@ -192,6 +192,9 @@ class PyNMF():
         if self.topo == '2d' and not hasattr(self, '_alg'):
             self._alg = nmf_algorithms_2D(self.A_ij, W, H, params=self.params)
         self.relative_err()
+        if getattr(self.params, 'err_monitor', False) and getattr(self, '_alg', None) is not None:
+            # opt-in: relative error after every iteration from the trace identity (no extra pass over A)
+            self.err_history = self._alg.monitor_history()
         if self.verbose == True:  # noqa: E712
             if self.rank == 0:
                 print('relative error is:', self.recon_err)

@@ -299,3 +299,22 @@ def test_resident_fit_limits():
     assert not ops.resident_fit_fits(8192, 4096, 4, 'kl', torch.float32)      # 128 MiB: the A-streaming path
     assert not ops.resident_fit_fits(96, 21, 65, 'fro', torch.float32)
     assert not ops.resident_fit_fits(96, 21, 4, 'l1', torch.float32)
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'float64'])
+@pytest.mark.parametrize('m,k', [(1, 1), (130, 3), (4100, 7), (70000, 32), (2048, 64)])
+def test_trace_terms(ops, m, k, dtype):
+    """dnmf_trace_terms: <W, V> and <G1, G2> in float64, and the device-side slot counter that appends to a history."""
+    rs = np.random.RandomState(5)
+    W, V = rs.rand(m, k).astype(dtype), rs.rand(m, k).astype(dtype)
+    G1, G2 = rs.rand(k, k).astype(dtype), rs.rand(k, k).astype(dtype)
+    ref = np.array([np.sum(W.astype(np.float64) * V.astype(np.float64)), np.sum(G1.astype(np.float64) * G2.astype(np.float64))])
+    dW, dV, dG1, dG2 = (torch.from_numpy(x).cuda() for x in (W, V, G1, G2))
+    got = ops.trace_terms(dW, dV, dG1, dG2).cpu().numpy()[0]
+    assert np.allclose(got, ref, rtol=1e-12, atol=0)
+    hist = torch.zeros((3, 2), dtype=torch.float64, device='cuda')
+    counter = torch.zeros(1, dtype=torch.int64, device='cuda')
+    for _ in range(5):                                   # two samples more than the history holds
+        ops.trace_terms(dW, dV, dG1, dG2, out=hist, slot_counter=counter)
+    assert int(counter.item()) == 5
+    assert np.allclose(hist.cpu().numpy(), np.tile(ref, (3, 1)), rtol=1e-12, atol=0)

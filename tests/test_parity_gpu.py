@@ -202,3 +202,23 @@ def test_ensemble_spread_over_ranks_equals_sequential():
     assert T.rel_fro(seq['Wall'][:, :, 2], ref[0]) <= 1e-4 and T.rel_fro(H2, ref[1]) <= 1e-4
     assert abs(seq['errs'][2] - float(ref[2])) <= 1e-5 * float(ref[2])
     assert np.isfinite(seq['col_err']).all() and seq['col_err'].shape == (21,)
+
+
+@pytest.mark.parametrize('name', ['u2048k32_2x1_fro_mu_i10', 'u2048k32_1x2_fro_mu_i10', 'u2048k32_2x2_fro_mu_i10',
+                                  'u4096x1024k32_1x1_fro_mu_i10', 'u64x48k4_4x2_fro_mu_i10_32'])
+def test_trace_identity_monitor_matches_direct_residual(name):
+    """params.err_monitor (dnmf_trace_terms): entry j-1 of the per-iteration history is the relative error after j
+    iterations, i.e. what a fit cut at j iterations returns from its direct residual pass; the monitored fit itself still
+    matches the reference golden."""
+    case = C.CASES_BY_NAME[name]
+    world = case['grid'][0] * case['grid'][1]
+    checkpoints = [1, 4, 9]
+    res = mp_util.run(world, workers.monitor_worker, (case, checkpoints), backend='gloo', timeout=900) if world > 1 \
+        else [workers.monitor_worker(0, 1, case, checkpoints)]
+    _compare(case, [r['full'] for r in res])
+    for r in res:
+        hist = r['full']['err_history']
+        assert hist is not None and len(hist) == case['itr'] - 1
+        for j in checkpoints:
+            # fp32 factors, float64 accumulation; err ~ 0.3-0.5 on these random matrices, no cancellation
+            assert abs(hist[j - 1] - r['err_at_%d' % j]) <= 2e-5 * r['err_at_%d' % j], (j, hist[j - 1], r['err_at_%d' % j])

@@ -95,6 +95,7 @@ def fit_worker(rank, world, case, force_generic=False, resident=True):
     args.norm, args.method, args.prune = case['norm'], case['method'], case['prune']
     args.W_update = case['W_update']
     args.resident_fit = resident
+    args.err_monitor = bool(case.get('err_monitor', False))
     blk = determine_block_params(rank, (p_r, p_c), A.shape).determine_block_index_range_asymm()
     A_ij = np.ascontiguousarray(A[blk[0][0]:blk[1][0] + 1, blk[0][1]:blk[1][1] + 1])
     factors = None
@@ -119,11 +120,29 @@ def fit_worker(rank, world, case, force_generic=False, resident=True):
     out = dict(W=np.asarray(W), H=np.asarray(H), err=float(err), err_dtype=str(np.asarray(err).dtype),
                tc_passes=int(n_tc), generic_passes=int(n_generic),
                peer_exchange=getattr(getattr(nmf, '_alg', None), '_px', None) is not None,
+               err_history=getattr(nmf, 'err_history', None),
                geom=[int(v) for v in (args.m, args.n, args.m_loc, args.n_loc, args.W_start, args.W_end,
                                       args.H_start, args.H_end)])
     if case['prune']:
         out.update(row_zero_idx_x=np.asarray(args.row_zero_idx_x), col_zero_idx_x=np.asarray(args.col_zero_idx_x),
                    row_zero_idx_w=np.asarray(args.row_zero_idx_w), col_zero_idx_h=np.asarray(args.col_zero_idx_h))
+    return out
+
+
+def monitor_worker(rank, world, case, checkpoints):
+    """PyNMF.fit with params.err_monitor on a parity case, plus plain fits cut short at `checkpoints` iterations: the
+    trace-identity history must reproduce the direct residual (relative_err) of those shorter fits."""
+    import copy
+    out = {}
+    c = copy.deepcopy(case)
+    c['err_monitor'] = True
+    full = fit_worker(rank, world, c)
+    out['full'] = full
+    for j in checkpoints:
+        cj = copy.deepcopy(case)
+        cj['itr'] = j
+        cj['expect_tc'] = False
+        out['err_at_%d' % j] = fit_worker(rank, world, cj)['err']
     return out
 
 
