@@ -62,25 +62,40 @@ constexpr int KL_CHUNK = KL_CHUNK_TILES;       // K-tiles accumulated in TMEM be
 // KL_PACKED = 1: the splitters' fp32 arithmetic uses the packed two-element instructions (FADD2 / FMUL2).
 // KL_S1 = 1: GEMM1 adds its three split terms into ONE 32-column accumulator (umma_tile_cat); the splitters then load
 // 32 S columns per row instead of 64 and skip an addition, and the freed tensor-memory columns deepen the rings.
+// KL_S1 = 2: the same single accumulator, but GEMM1 works on PAIRS of tiles (64 reduced indices): twelve N = 64 MMAs per
+// pair (K-concatenated hi.hi + hi.lo + lo.hi) fill columns [0,32) with the S tile of the even tile and [32,64) with the
+// odd one's.  N = 64 runs at the tensor pipe's full rate (an N = 32 MMA costs 22 cycles instead of 16, which is what made
+// KL_S1 = 1 slower), the splitters load half the S columns, and one S slot / one factor-tile slot serves two tiles.
 #ifndef KL_PACKED
 #define KL_PACKED 1
 #endif
 #ifndef KL_S1
-#define KL_S1 0       // measured slower on B200 (12 N=32 MMAs cost more tensor-pipe time than 4 x {N=64, N=32})
+#define KL_S1 2       // round 2: 0 -> 2 is -6 % (UHT) / -0 % (WTU) isolated, -3 % sustained; 1 is slower than 0 (N = 32 MMA floor)
 #endif
 
 struct KlCfg {
   static constexpr int N2 = 2 * KK;                    // 64
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;    // 16 KB
   static constexpr int B_BYTES = N2 * TC_BK * 4;       // 8 KB  Bcat tile  [2k][32 r]
-  static constexpr int F_BYTES = N2 * KK * 4;          // 8 KB  FrCat tile [hi 32 r | lo 32 r][k]
+#if KL_S1 == 2
+  static constexpr int F_ROWS = 2 * TC_BK;             // reduced indices per factor tile: a pair of tiles
+#else
+  static constexpr int F_ROWS = TC_BK;
+#endif
+  static constexpr int F_BYTES = 2 * F_ROWS * KK * 4;  // FrCat tile [hi F_ROWS r | lo F_ROWS r][k]: 8 KB, 16 KB for pairs
 #ifndef KL_SA
 #define KL_SA 8
 #define KL_SB 4
+#if KL_S1 == 2
+#define KL_SF 2
+#else
 #define KL_SF 4
 #endif
+#endif
   static constexpr int SA = KL_SA, SB = KL_SB, SF = KL_SF;
-#if KL_S1
+#if KL_S1 == 2
+  static constexpr int NBUF = 2, NT = 3, NS = 2, S_COLS = 2 * KK;       // one S slot = the S tiles of a pair
+#elif KL_S1
   static constexpr int NBUF = 2, NT = 3, NS = 4, S_COLS = KK;
 #else
 #ifndef KL_NT
@@ -105,7 +120,12 @@ struct KlCfg {
   // completed.  The group knows that for every tile up to its own previous one (tile - KL_GROUPS; GEMM1 and GEMM2 complete
   // in tile order), and the slot's previous use is tile - NS (resp. tile - NT): both rings need at least KL_GROUPS slots,
   // otherwise a group that runs ahead passes the wait one phase early (observed as a hang with NS = 2 and 3 groups).
+#if KL_S1 == 2
+  // (pairs: the slot's previous use is pair p - NS and the group knows every pair up to p - ceil(KL_GROUPS / 2) complete)
+  static_assert(2 * NS >= KL_GROUPS + 1 && NT >= KL_GROUPS, "S and operand rings too shallow for the splitter groups");
+#else
   static_assert(NS >= KL_GROUPS && NT >= KL_GROUPS, "S and operand rings need one slot per splitter group");
+#endif
   static constexpr int NBARS = 2 * SA + 2 * SB + 2 * SF + 2 * NT + 2 * NS + 2 * NBUF + 2;
   static constexpr int BAR_BYTES = 1024;
   static_assert((NBARS + 1) * 8 <= BAR_BYTES, "barrier area too small");
@@ -157,7 +177,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < SB; ++s) { mbar_init(bar(iBF + s), 1); mbar_init(bar(iBE + s), 1); }
     for (int s = 0; s < SF; ++s) { mbar_init(bar(iFF + s), 1); mbar_init(bar(iFE + s), 1); }
     for (int s = 0; s < NT; ++s) { mbar_init(bar(iTF + s), 4); mbar_init(bar(iTE + s), 1); }
-    for (int s = 0; s < NS; ++s) { mbar_init(bar(iSF + s), 1); mbar_init(bar(iSE + s), 4); }
+    for (int s = 0; s < NS; ++s) { mbar_init(bar(iSF + s), 1); mbar_init(bar(iSE + s), KL_S1 == 2 ? 8 : 4); }
     for (int b = 0; b < NBUF; ++b) { mbar_init(bar(iCF + b), 1); mbar_init(bar(iCE + b), 4); }
     mbar_init(bar(iXF), 4);
     mbar_init(bar(iXE), 1);
@@ -242,7 +262,8 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int sp = unit / x_blocks;
         const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
-        for (int kt = kt0; kt < kt1; ++kt) {
+        // one factor tile per K tile, or per PAIR of K tiles (KL_S1 == 2: the TMA box then has 64 rows)
+        for (int kt = kt0; kt < kt1; kt += (KL_S1 == 2 ? 2 : 1)) {
           mbar_wait(bar(iFE + s), ph ^ 1u);
           if (dbg & 0x20000) { mbar_arrive(bar(iFF + s)); if (++s == SF) { s = 0; ph ^= 1u; } continue; }   // ablation
           mbar_expect_tx(bar(iFF + s), Cfg::F_BYTES);
@@ -268,15 +289,20 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int kt0 = sp * kt_per_split, kt1 = min(kt_total, kt0 + kt_per_split);
       const int ntiles = kt1 - kt0;
       mbar_wait(bar(iXF), pxu);                     // this unit's Fx block is in tensor memory
-      for (int j = 0; j < ntiles; ++j) {
+      constexpr int JSTEP = (KL_S1 == 2) ? 2 : 1;
+      for (int j = 0; j < ntiles; j += JSTEP) {
         mbar_wait(bar(iFF + sf), pf);
         mbar_wait(bar(iSE + ss), ps ^ 1u);
         TC_T(t_g1wait);
         tc_fence_after();
         if (dbg & 4)
-          umma_commits_only(bar(iSF + ss), bar(iFE + sf), bar(iXE), (j == ntiles - 1) ? 1u : 0u);
+          umma_commits_only(bar(iSF + ss), bar(iFE + sf), bar(iXE), (j + JSTEP >= ntiles) ? 1u : 0u);
         else
-#if KL_S1
+#if KL_S1 == 2
+          umma_tile_cat<2 * KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS), fx_tmem,
+                                make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), idesc_full,
+                                bar(iSF + ss), bar(iFE + sf), bar(iXE), (j + JSTEP >= ntiles) ? 1u : 0u);
+#elif KL_S1
           umma_tile_cat<KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS), fx_tmem,
                             make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), idesc_half,
                             bar(iSF + ss), bar(iFE + sf), bar(iXE), (j == ntiles - 1) ? 1u : 0u);
@@ -343,6 +369,8 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int r = q * 32 + lane;
     const int group = split_group;
     int tile = 0;
+    int pair_base = 0;                      // KL_S1 == 2: tile pairs of the units this CTA has finished
+    (void)pair_base;
     uint32_t pxe = 0;
     double res_sum = 0.0, a_sum = 0.0;      // MODE 2 only
     long long tprev = clock64(), t_afull = 0, t_load = 0, t_sfull = 0, t_div = 0, t_tfree = 0, t_store = 0;
@@ -374,8 +402,21 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       for (int kt = kt0; kt < kt1; ++kt, ++tile) {
         if (tile % KL_GROUPS != group) continue;
-        const int sa = tile % SA, ts = tile % NT, ss = tile % NS;
-        const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u, ps = (uint32_t)(tile / NS) & 1u;
+        const int sa = tile % SA, ts = tile % NT;
+        const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u;
+#if KL_S1 == 2
+        // S slots hold PAIRS of tiles: pair index inside this CTA's sequence, which half of the slot is this tile's, and
+        // whether the tile has no partner (odd tile count of the unit: it then releases the slot for both)
+        const int jt = kt - kt0;
+        const int pairid = pair_base + (jt >> 1);
+        const int ss = pairid % NS, s_half = jt & 1;
+        const uint32_t ps = (uint32_t)(pairid / NS) & 1u;
+        const bool s_lone = (s_half == 0) && (kt == kt1 - 1);
+#else
+        const int ss = tile % NS, s_half = 0;
+        const uint32_t ps = (uint32_t)(tile / NS) & 1u;
+        const bool s_lone = false;
+#endif
         TC_T(t_store);
         mbar_wait(bar(iAF + sa), pa);
         TC_T(t_afull);
@@ -413,7 +454,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (q == 0 && lane == 0 && !(dbg & 4)) mbar_arrive(bar(iFE + tile % SF));
 #endif
         tc_fence_after();
-        const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS);
+        const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS + s_half * KK);
         {
 #if KL_S1
           uint32_t s0[32];
@@ -455,11 +496,21 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) {
               mbar_arrive(bar(iSE + ss));       // S slot may be overwritten
+              if (s_lone) mbar_arrive(bar(iSE + ss));
               mbar_arrive(bar(iAE + sa));       // every register loaded from the A tile has been consumed above
             }
             continue;
           }
-#if KL_PACKED && !KL_S1
+#if KL_PACKED && KL_S1
+#pragma unroll
+          for (int j = 0; MODE != 3 && j < 32; j += 2) {
+            const float2 den = __fadd2_rn(make_float2(__uint_as_float(s0[j]), __uint_as_float(s0[j + 1])), make_float2(eps, eps));
+            const float2 q2 = (dbg & 1) ? den : make_float2(rcp_approx(den.x), rcp_approx(den.y));
+            const float2 uu = __fmul2_rn(make_float2(__uint_as_float(u[j]), __uint_as_float(u[j + 1])), q2);
+            u[j] = __float_as_uint(uu.x);
+            u[j + 1] = __float_as_uint(uu.y);
+          }
+#elif KL_PACKED
           // two elements per FADD2 / FMUL2 (sm_100 packed fp32): the same roundings as the scalar code below, half the
           // FMA-pipe instructions of the warps whose instruction stream sets the pass time
 #pragma unroll
@@ -486,7 +537,10 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(iSE + ss));          // S slot may be overwritten
+        if (lane == 0) {
+          mbar_arrive(bar(iSE + ss));                       // S slot may be overwritten
+          if (s_lone) mbar_arrive(bar(iSE + ss));           // ... on behalf of the missing odd tile as well
+        }
 #if KL_PACKED
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -521,6 +575,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iTF + ts));
       }
+      pair_base += (kt1 - kt0 + 1) >> 1;
     }
     if (MODE == 2 || MODE == 3) {
       // one (residual, norm) pair per splitter thread; summed in a fixed order by the caller
@@ -703,7 +758,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   if (rc) return rc;
   rc = tc_make_map(&tmB, Bcat, 2 * KK, r_len, pl.ldb, TC_BK, 2 * KK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const int64_t split_stride = x_len * KK;
   // (for UHT the x-side factor rows are read straight from W with its own leading dimension: only k_real columns exist)
@@ -767,7 +822,7 @@ int tc_ah_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw,
   if (rc) return rc;
   rc = tc_make_map(&tmB, Bcat, 2 * KK, n, pl.ldb, TC_BK, 2 * KK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   auto kern = tc_kl_kernel<3>;
   static bool attr_set = false;
@@ -821,7 +876,7 @@ int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, co
   alignas(64) CUtensorMap tmA, tmF;
   int rc = tc_make_map(&tmA, A, m, n, lda, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   auto kern = tc_kl_kernel<2>;
   static bool attr_set = false;
