@@ -295,6 +295,33 @@ int dnmf_ah_residual(const void* A, int64_t lda, const void* W, int64_t ldw, con
                      int64_t ldv, int64_t m, int64_t n, int64_t k, double* out, int dtype, void* ws, int64_t ws_bytes,
                      void* stream);
 
+/* ---- update fused with the pass's split reduction ("fused epilogue") ------------------------------------------------
+ * An A-streaming pass is split over the reduced dimension (deterministic split-K); dnmf_ah / dnmf_wta / dnmf_kl_* end with
+ * a launch that sums the per-split partials into V / Y, which the update kernel then reads back.  The _p variants leave
+ * the partials in the workspace and describe them in view4 = {device pointer of P[split][x][ldp], ldp, splits,
+ * split stride (elements)}; the _p updates (and the row grid's exchange) take that view and add the splits themselves in
+ * the same order: bit-identical results, one launch and one factor-sized HBM round trip less per half-step
+ * (dist_nmf.py:730-732, :749-751, :806-830, :808-849 as pass + update = 2 launches).
+ * The pass variants return DNMF_E_UNSUPPORTED, without side effects, when the call is not served by the tcgen05 path
+ * (fp64, small or unaligned shards, KL with k > 32): the caller then uses the plain entry points.  fp32 only.
+ * The view is valid until the next call that uses the same workspace. */
+int dnmf_ah_p(const void* A, int64_t lda, const void* H, int64_t ldh, int64_t m, int64_t n, int64_t k, int dtype,
+              int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream);
+int dnmf_wta_p(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t m, int64_t n, int64_t k, int dtype,
+               int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream);
+int dnmf_kl_uht_p(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh, int64_t m, int64_t n,
+                  int64_t k, double eps, int dtype, int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream);
+int dnmf_kl_wtu_p(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh, int64_t m, int64_t n,
+                  int64_t k, double eps, int dtype, int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream);
+int dnmf_mu_update_w_p(void* W, int64_t ldw, const int64_t* view4, const void* G, int64_t m, int64_t k, double eps,
+                       int dtype, void* stream);
+int dnmf_mu_update_h_p(void* H, int64_t ldh, const int64_t* view4, const void* G, int64_t k, int64_t n, double eps,
+                       int clamp, int dtype, void* stream);
+int dnmf_kl_update_w_p(void* W, int64_t ldw, const int64_t* view4, const void* x, int64_t m, int64_t k, double eps,
+                       int dtype, void* stream);
+int dnmf_kl_update_h_p(void* H, int64_t ldh, const int64_t* view4, const void* x, int64_t k, int64_t n, double eps,
+                       int clamp, int dtype, void* stream);
+
 /* ---- FRO-BCD with its scalars on the device (dist_nmf.py:996-1047): the same arithmetic as dnmf_bcd_pg_w / _h with the
  * Lipschitz bound read from device memory, and the iteration's control state (Lipschitz bounds, objective, momentum
  * weights, accept / restore decision) kept in a 16-double device vector:
@@ -360,6 +387,9 @@ int dnmf_symm_free(void* ptr);
 int64_t dnmf_xchg_bytes(int nranks, int64_t n, int64_t k, int dtype);
 int dnmf_xchg_update_h(void* const* bases, int nranks, int me, int mode, void* H, int64_t ldh, const void* Yt, int64_t ldy,
                        const void* aux, int64_t n, int64_t k, double p0, int clamp, int dtype, void* stream);
+/* the same with this rank's partial given as the split-K partials of dnmf_wta_p / dnmf_kl_wtu_p (view4, see above) */
+int dnmf_xchg_update_h_p(void* const* bases, int nranks, int me, int mode, void* H, int64_t ldh, const int64_t* view4,
+                         const void* aux, int64_t n, int64_t k, double p0, int clamp, int dtype, void* stream);
 int dnmf_xchg_error(const void* local_region, int* error_out, void* stream);
 
 /* HALS W sweep (dist_nmf.py:888-893, 2-D :427-432) as ONE cooperative launch: the k Gauss-Seidel column updates with

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get('DNMF_LIB_PATH') or os.path.join(_HERE, 'libdnmf.so') 
 
 F32, F64, I64 = 0, 1, 2
 MATH_ACCURATE, MATH_TF32 = 0, 1
+E_UNSUPPORTED = -2
 OP_AH, OP_WTA, OP_KL_UHT, OP_KL_WTU, OP_GRAM, OP_RESIDUAL, OP_SUMS, OP_NNZ, OP_AH_RESIDUAL = range(9)
 MAX_K = 64
 
@@ -45,6 +46,14 @@ SIGNATURES = {
     'dnmf_rowsum': (i32, [vp, i64, i64, i64, vp, i32, vp, i64, vp]),
     'dnmf_sqnorm': (i32, [vp, i64, i64, i64, vp, i32, vp, i64, vp]),
     'dnmf_normalize': (i32, [vp, i64, i64, vp, i64, i64, i64, vp, dbl, i32, vp]),
+    'dnmf_ah_p': (i32, [vp, i64, vp, i64, i64, i64, i64, i32, i32, vp, i64, vp, vp]),
+    'dnmf_wta_p': (i32, [vp, i64, vp, i64, i64, i64, i64, i32, i32, vp, i64, vp, vp]),
+    'dnmf_kl_uht_p': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, dbl, i32, i32, vp, i64, vp, vp]),
+    'dnmf_kl_wtu_p': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, dbl, i32, i32, vp, i64, vp, vp]),
+    'dnmf_mu_update_w_p': (i32, [vp, i64, vp, vp, i64, i64, dbl, i32, vp]),
+    'dnmf_mu_update_h_p': (i32, [vp, i64, vp, vp, i64, i64, dbl, i32, i32, vp]),
+    'dnmf_kl_update_w_p': (i32, [vp, i64, vp, vp, i64, i64, dbl, i32, vp]),
+    'dnmf_kl_update_h_p': (i32, [vp, i64, vp, vp, i64, i64, dbl, i32, i32, vp]),
     'dnmf_trace_terms_workspace_bytes': (i64, []),
     'dnmf_trace_terms': (i32, [vp, i64, vp, i64, i64, vp, vp, i64, vp, vp, i64, i32, vp, i64, vp]),
     'dnmf_residual_sqnorm': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp, i32, vp, i64, vp]),
@@ -103,6 +112,7 @@ SIGNATURES = {
     'dnmf_xchg_bytes': (i64, [i32, i64, i64, i32]),
     'dnmf_xchg_error': (i32, [vp, C.POINTER(i32), vp]),
     'dnmf_xchg_update_h': (i32, [C.POINTER(vp), i32, i32, i32, vp, i64, vp, i64, vp, i64, i64, dbl, i32, i32, vp]),
+    'dnmf_xchg_update_h_p': (i32, [C.POINTER(vp), i32, i32, i32, vp, i64, vp, vp, i64, i64, dbl, i32, i32, vp]),
     'dnmf_hals_w_sweep': (i32, [vp, i64, vp, i64, vp, i64, i64, dbl, C.POINTER(vp), i32, i32, i64, vp, i64, i32, vp]),
     'dnmf_mu_fit_resident_smem_bytes': (i64, [i64, i64, i64, i32, i32]),
     'dnmf_mu_fit_resident_cluster_size': (i32, [i64, i64, i64, i32, i32]),

@@ -251,7 +251,7 @@ int dnmf_kl_update_w(void* W, int64_t ldw, const void* V, int64_t ldv, const voi
   DNMF_CHECK_ARG(W && V && x, "null pointer");
   if (m == 0 || k == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_T(dtype, (kl_update_w_kernel<T><<<(unsigned)ceil_div(m * k, 256), 256, 0, st>>>((T*)W, ldw, (const T*)V, ldv, (const T*)x, m, (int)k, (T)eps)));
+  DISPATCH_T(dtype, (kl_update_w_kernel<T><<<(unsigned)ceil_div(m * k, 256), 256, 0, st>>>((T*)W, ldw, (const T*)V, ldv, (const T*)x, m, (int)k, (T)eps, 1, 0)));
   DNMF_LAUNCH_CHECK("kl_update_w_kernel");
   return 0;
 }
@@ -262,10 +262,116 @@ int dnmf_kl_update_h(void* H, int64_t ldh, const void* Y, int64_t y_stride_k, in
   DNMF_CHECK_ARG(H && Y && x, "null pointer");
   if (n == 0 || k == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_T(dtype, (kl_update_h_kernel<T><<<(unsigned)ceil_div(k * n, 256), 256, 0, st>>>((T*)H, ldh, (const T*)Y, y_stride_k, y_stride_c, (const T*)x, (int)k, n, (T)eps, clamp)));
+  DISPATCH_T(dtype, (kl_update_h_kernel<T><<<(unsigned)ceil_div(k * n, 256), 256, 0, st>>>((T*)H, ldh, (const T*)Y, y_stride_k, y_stride_c, (const T*)x, (int)k, n, (T)eps, clamp, 1, 0)));
   DNMF_LAUNCH_CHECK("kl_update_h_kernel");
   return 0;
 }
+
+// ---- deferred split reduction: pass -> partial view -> update that sums the splits itself -----------------------------
+namespace {
+int fill_view(const TcPartials& d, int64_t* view4) {
+  view4[0] = (int64_t)(uintptr_t)d.P; view4[1] = d.ldp; view4[2] = d.splits; view4[3] = d.split_stride;
+  return 0;
+}
+}  // namespace
+
+int dnmf_ah_p(const void* A, int64_t lda, const void* H, int64_t ldh, int64_t m, int64_t n, int64_t k, int dtype,
+              int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream) {
+  if (int rc = check_common(m, n, k, dtype)) return rc;
+  DNMF_CHECK_ARG(A && H && view4, "null pointer");
+  if (m == 0 || k == 0 || !tc_eligible(DNMF_OP_AH, A, lda, m, n, k, dtype)) return DNMF_E_UNSUPPORTED;
+  tls().last_path = 1;
+  tls().tc_passes++;
+  TcPartials d;
+  if (int rc = tc_ah((const float*)A, lda, (const float*)H, ldh, nullptr, 0, m, n, (int)k, math_mode, ws, ws_bytes, (cudaStream_t)stream, &d)) return rc;
+  return fill_view(d, view4);
+}
+
+int dnmf_wta_p(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t m, int64_t n, int64_t k, int dtype,
+               int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream) {
+  if (int rc = check_common(m, n, k, dtype)) return rc;
+  DNMF_CHECK_ARG(A && W && view4, "null pointer");
+  if (n == 0 || k == 0 || !tc_eligible(DNMF_OP_WTA, A, lda, m, n, k, dtype)) return DNMF_E_UNSUPPORTED;
+  tls().last_path = 1;
+  tls().tc_passes++;
+  TcPartials d;
+  if (int rc = tc_wta((const float*)A, lda, (const float*)W, ldw, nullptr, 0, m, n, (int)k, 1, math_mode, ws, ws_bytes, (cudaStream_t)stream, &d)) return rc;
+  return fill_view(d, view4);
+}
+
+int dnmf_kl_uht_p(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh, int64_t m, int64_t n,
+                  int64_t k, double eps, int dtype, int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream) {
+  if (int rc = check_common(m, n, k, dtype)) return rc;
+  DNMF_CHECK_ARG(A && W && H && view4, "null pointer");
+  if (m == 0 || k == 0 || !tc_eligible(DNMF_OP_KL_UHT, A, lda, m, n, k, dtype)) return DNMF_E_UNSUPPORTED;
+  tls().last_path = 1;
+  tls().tc_passes++;
+  TcPartials d;
+  if (int rc = tc_kl_uht((const float*)A, lda, (const float*)W, ldw, (const float*)H, ldh, nullptr, 0, m, n, (int)k, (float)eps, math_mode, ws, ws_bytes, (cudaStream_t)stream, &d)) return rc;
+  return fill_view(d, view4);
+}
+
+int dnmf_kl_wtu_p(const void* A, int64_t lda, const void* W, int64_t ldw, const void* H, int64_t ldh, int64_t m, int64_t n,
+                  int64_t k, double eps, int dtype, int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream) {
+  if (int rc = check_common(m, n, k, dtype)) return rc;
+  DNMF_CHECK_ARG(A && W && H && view4, "null pointer");
+  if (n == 0 || k == 0 || !tc_eligible(DNMF_OP_KL_WTU, A, lda, m, n, k, dtype)) return DNMF_E_UNSUPPORTED;
+  tls().last_path = 1;
+  tls().tc_passes++;
+  TcPartials d;
+  if (int rc = tc_kl_wtu((const float*)A, lda, (const float*)W, ldw, (const float*)H, ldh, nullptr, 0, m, n, (int)k, (float)eps, 1, math_mode, ws, ws_bytes, (cudaStream_t)stream, &d)) return rc;
+  return fill_view(d, view4);
+}
+
+#define DNMF_VIEW(view4)                                                                                         \
+  DNMF_CHECK_ARG((view4) && (view4)[0] && (view4)[2] >= 1, "bad partial view");                                   \
+  const float* vp_ = reinterpret_cast<const float*>((uintptr_t)(view4)[0]);                                      \
+  const int64_t vld_ = (view4)[1], vss_ = (view4)[3];                                                            \
+  const int vsp_ = (int)(view4)[2]
+
+int dnmf_mu_update_w_p(void* W, int64_t ldw, const int64_t* view4, const void* G, int64_t m, int64_t k, double eps,
+                       int dtype, void* stream) {
+  if (int rc = check_common(m, 0, k, dtype)) return rc;
+  DNMF_CHECK_ARG(W && G && dtype == DNMF_F32, "null pointer / partial views are fp32");
+  DNMF_VIEW(view4);
+  if (m == 0 || k == 0) return 0;
+  return row_update_dispatch<float>(0, (float*)W, ldw, (const float*)W, ldw, vp_, vld_, (const float*)G, m, (int)k, (float)eps, nullptr, (cudaStream_t)stream, vsp_, vss_);
+}
+
+int dnmf_mu_update_h_p(void* H, int64_t ldh, const int64_t* view4, const void* G, int64_t k, int64_t n, double eps,
+                       int clamp, int dtype, void* stream) {
+  if (int rc = check_common(0, n, k, dtype)) return rc;
+  DNMF_CHECK_ARG(H && G && dtype == DNMF_F32, "null pointer / partial views are fp32");
+  DNMF_VIEW(view4);
+  if (n == 0 || k == 0) return 0;
+  // partial layout [x = column][ldp]: stride 1 between factor rows, ldp between columns
+  return col_update_dispatch<float>(0, (float*)H, ldh, (const float*)H, ldh, vp_, 1, vld_, (const float*)G, (int)k, n, (float)eps, clamp, nullptr, (cudaStream_t)stream, vsp_, vss_);
+}
+
+int dnmf_kl_update_w_p(void* W, int64_t ldw, const int64_t* view4, const void* x, int64_t m, int64_t k, double eps,
+                       int dtype, void* stream) {
+  if (int rc = check_common(m, 0, k, dtype)) return rc;
+  DNMF_CHECK_ARG(W && x && dtype == DNMF_F32, "null pointer / partial views are fp32");
+  DNMF_VIEW(view4);
+  if (m == 0 || k == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  kl_update_w_kernel<float><<<(unsigned)ceil_div(m * k, 256), 256, 0, st>>>((float*)W, ldw, vp_, vld_, (const float*)x, m, (int)k, (float)eps, vsp_, vss_);
+  DNMF_LAUNCH_CHECK("kl_update_w_kernel<p>");
+  return 0;
+}
+
+int dnmf_kl_update_h_p(void* H, int64_t ldh, const int64_t* view4, const void* x, int64_t k, int64_t n, double eps,
+                       int clamp, int dtype, void* stream) {
+  if (int rc = check_common(0, n, k, dtype)) return rc;
+  DNMF_CHECK_ARG(H && x && dtype == DNMF_F32, "null pointer / partial views are fp32");
+  DNMF_VIEW(view4);
+  if (n == 0 || k == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  kl_update_h_kernel<float><<<(unsigned)ceil_div(k * n, 256), 256, 0, st>>>((float*)H, ldh, vp_, 1, vld_, (const float*)x, (int)k, n, (float)eps, clamp, vsp_, vss_);
+  DNMF_LAUNCH_CHECK("kl_update_h_kernel<p>");
+  return 0;
+}
+#undef DNMF_VIEW
 
 int dnmf_clamp_min(void* X, int64_t ldx, int64_t rows, int64_t cols, double lo, int dtype, void* stream) {
   if (int rc = check_common(rows, cols, 0, dtype)) return rc;

@@ -164,9 +164,11 @@ __device__ __forceinline__ void publish_when_grid_done(const XchgBases& B, XchgC
 
 // push: rows [q n_chunk, (q+1) n_chunk) of the local Yt [n x k] -> recv[me] of owner q; aux (aux_len values) -> aux[me]
 // of every rank.  grid-stride over the n x k elements.
+// (Yt may be given as `splits` split-K partials `sstride` elements apart: summed here in split order, see sum_splits)
 template <typename T>
 __global__ void __launch_bounds__(256) xchg_push_kernel(XchgBases B, XchgLayout L, int P, int me, const T* __restrict__ Yt,
-                                                        int64_t ldy, int64_t n, int k, const T* __restrict__ aux, int aux_len) {
+                                                        int64_t ldy, int64_t n, int k, const T* __restrict__ aux, int aux_len,
+                                                        int splits, int64_t sstride) {
   XchgCtrl* ctrl = reinterpret_cast<XchgCtrl*>(B.p[me]);
   const unsigned int epoch = ctrl->epoch + 1u;          // every CTA reads the value left by the previous exchange
   const int64_t total = n * k;
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(256) xchg_push_kernel(XchgBases B, XchgLayout 
     const int j = (int)(idx % k);
     const int q = (int)(c / L.n_chunk);
     T* recv = reinterpret_cast<T*>(B.p[q] + L.off_recv) + ((int64_t)me * L.n_chunk + (c - (int64_t)q * L.n_chunk)) * k;
-    recv[j] = Yt[c * ldy + j];
+    recv[j] = sum_splits(Yt + c * ldy + j, splits, sstride);
   }
   if (blockIdx.x < (unsigned)P) {                        // CTA q delivers the small operand to rank q
     T* dst = reinterpret_cast<T*>(B.p[blockIdx.x] + L.off_aux) + (int64_t)me * k * k;
@@ -560,8 +562,9 @@ int dnmf_xchg_error(const void* local_region, int* error_out, void* stream) {
 // One H half-step: H (k x n, replicated) <- update(H, sum_q Yt_q, sum_q aux_q).  mode 0 FRO-MU (aux = local W^T W,
 // p0 = eps), 2 FRO-HALS (aux = local W^T W, p0 = eps), 3 KL-MU (aux = local colsum(W), p0 = eps).
 // bases[q] = rank q's exchange region as mapped here (bases[me] = the local allocation).
-int dnmf_xchg_update_h(void* const* bases, int nranks, int me, int mode, void* H, int64_t ldh, const void* Yt, int64_t ldy,
-                       const void* aux, int64_t n, int64_t k, double p0, int clamp, int dtype, void* stream) {
+static int xchg_update_h_impl(void* const* bases, int nranks, int me, int mode, void* H, int64_t ldh, const void* Yt, int64_t ldy,
+                              int splits, int64_t sstride, const void* aux, int64_t n, int64_t k, double p0, int clamp, int dtype,
+                              void* stream) {
   DNMF_CHECK_ARG(bases && H && Yt && aux, "null pointer");
   DNMF_CHECK_ARG(nranks >= 1 && nranks <= XCHG_MAX_P && me >= 0 && me < nranks, "bad rank count");
   DNMF_CHECK_ARG(mode == 0 || mode == 2 || mode == 3, "mode must be 0 (FRO-MU), 2 (FRO-HALS) or 3 (KL-MU)");
@@ -579,7 +582,7 @@ int dnmf_xchg_update_h(void* const* bases, int nranks, int me, int mode, void* H
 #define DNMF_XCHG_T(T)                                                                                                        \
   do {                                                                                                                        \
     xchg_push_kernel<T><<<push_grid < (unsigned)nranks ? (unsigned)nranks : push_grid, 256, 0, st>>>(                         \
-        B, L, nranks, me, (const T*)Yt, ldy, n, (int)k, (const T*)aux, aux_len);                                              \
+        B, L, nranks, me, (const T*)Yt, ldy, n, (int)k, (const T*)aux, aux_len, splits, sstride);                             \
     DNMF_LAUNCH_CHECK("xchg_push_kernel");                                                                                    \
     DNMF_DISPATCH_KP(kp, {                                                                                                    \
       if (mode == 0) xchg_update_kernel<T, KP, 0><<<upd_grid, kColUpdThreads, 0, st>>>(B, L, nranks, me, (const T*)H, ldh, n, (int)k, (T)p0, clamp); \
@@ -596,6 +599,18 @@ int dnmf_xchg_update_h(void* const* bases, int nranks, int me, int mode, void* H
   xchg_epoch_kernel<<<1, 1, 0, st>>>(reinterpret_cast<XchgCtrl*>(B.p[me]));
   DNMF_LAUNCH_CHECK("xchg_epoch_kernel");
   return 0;
+}
+
+int dnmf_xchg_update_h(void* const* bases, int nranks, int me, int mode, void* H, int64_t ldh, const void* Yt, int64_t ldy,
+                       const void* aux, int64_t n, int64_t k, double p0, int clamp, int dtype, void* stream) {
+  return xchg_update_h_impl(bases, nranks, me, mode, H, ldh, Yt, ldy, 1, 0, aux, n, k, p0, clamp, dtype, stream);
+}
+
+int dnmf_xchg_update_h_p(void* const* bases, int nranks, int me, int mode, void* H, int64_t ldh, const int64_t* view4,
+                         const void* aux, int64_t n, int64_t k, double p0, int clamp, int dtype, void* stream) {
+  DNMF_CHECK_ARG(view4 && view4[0] && view4[2] >= 1, "bad partial view");
+  return xchg_update_h_impl(bases, nranks, me, mode, H, ldh, reinterpret_cast<const void*>((uintptr_t)view4[0]), view4[1],
+                            (int)view4[2], view4[3], aux, n, k, p0, clamp, dtype, stream);
 }
 
 // HALS W sweep, one launch.  nranks == 1 (or bases == NULL): single rank, `scratch` must hold k * 1024 doubles + 1 uint32

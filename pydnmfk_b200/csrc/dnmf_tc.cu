@@ -490,7 +490,8 @@ int launch_pass_k(int k, const CUtensorMap& tmA, const CUtensorMap& tmB, float* 
 
 // V (AH) or Y / Y^T (WTA) through the tensor path.  ws = [Bcat | partials]
 int tc_run(int mode, const float* A, int64_t lda, const float* B, int64_t ldbsrc, float* out, int64_t ldo,
-           int64_t m, int64_t n, int k, int transposed_out, int hi_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
+           int64_t m, int64_t n, int k, int transposed_out, int hi_mode, void* ws, int64_t ws_bytes, cudaStream_t st,
+           TcPartials* defer) {
   const int64_t x_len = mode == 0 ? m : n;
   const int64_t r_len = mode == 0 ? n : m;
   const int kp = tc_padded_k(k);      // the kernels exist for 16 / 32 / 64 factor columns: smaller k ride along zero-padded
@@ -523,6 +524,10 @@ int tc_run(int mode, const float* A, int64_t lda, const float* B, int64_t ldbsrc
   rc = mode == 0 ? launch_pass_k<0>(kp, tmA, tmB, P, split_stride, x_len, pl, hi_mode, st)
                  : launch_pass_k<1>(kp, tmA, tmB, P, split_stride, x_len, pl, hi_mode, st);
   if (rc) return rc;
+  if (defer != nullptr) {      // the consumer (an update kernel) sums the splits itself, in the same order
+    defer->P = P; defer->ldp = kp; defer->split_stride = split_stride; defer->splits = pl.splits;
+    return 0;
+  }
   // fixed-order sum of the split partials P[s][x][kk]  ->  out  (only the k real columns)
   int64_t so_r, so_c;   // strides of (x, kk) in the output
   if (mode == 0) { so_r = ldo; so_c = 1; }                        // V[x][kk]
@@ -563,7 +568,7 @@ void calibrate() {
   for (int mode = 0; mode < 1; ++mode) {      // only the truncating split is compiled into the kernels
     cudaMemset(dV, 0, m * k * 4);
     const int64_t saved = tls().launches;
-    int rc = tc_run(0, dA, n, dH, n, dV, k, m, n, k, 0, mode, dws, wsb, 0);
+    int rc = tc_run(0, dA, n, dH, n, dV, k, m, n, k, 0, mode, dws, wsb, 0, nullptr);
     tls().launches = saved;
     if (rc != 0 || cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); break; }
     cudaMemcpy(hV, dV, m * k * 4, cudaMemcpyDeviceToHost);
@@ -647,23 +652,24 @@ int64_t tc_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype) {
 }
 
 int tc_ah(const float* A, int64_t lda, const float* H, int64_t ldh, float* V, int64_t ldv, int64_t m, int64_t n, int k,
-          int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  return tc_run(0, A, lda, H, ldh, V, ldv, m, n, k, 0, g_hi_mode, ws, ws_bytes, st);
+          int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st, TcPartials* defer) {
+  return tc_run(0, A, lda, H, ldh, V, ldv, m, n, k, 0, g_hi_mode, ws, ws_bytes, st, defer);
 }
 
 int tc_wta(const float* A, int64_t lda, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t m, int64_t n, int k,
-           int transposed_out, int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  return tc_run(1, A, lda, W, ldw, Y, ldy, m, n, k, transposed_out, g_hi_mode, ws, ws_bytes, st);
+           int transposed_out, int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st, TcPartials* defer) {
+  return tc_run(1, A, lda, W, ldw, Y, ldy, m, n, k, transposed_out, g_hi_mode, ws, ws_bytes, st, defer);
 }
 
 int tc_kl_uht(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* V, int64_t ldv,
-              int64_t m, int64_t n, int k, float eps, int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  return tc_kl_run(0, A, lda, W, ldw, H, ldh, V, ldv, m, n, k, eps, 0, ws, ws_bytes, st);
+              int64_t m, int64_t n, int k, float eps, int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st,
+              TcPartials* defer) {
+  return tc_kl_run(0, A, lda, W, ldw, H, ldh, V, ldv, m, n, k, eps, 0, ws, ws_bytes, st, defer);
 }
 int tc_kl_wtu(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* Y, int64_t ldy,
               int64_t m, int64_t n, int k, float eps, int transposed_out, int math_mode, void* ws, int64_t ws_bytes,
-              cudaStream_t st) {
-  return tc_kl_run(1, A, lda, W, ldw, H, ldh, Y, ldy, m, n, k, eps, transposed_out, ws, ws_bytes, st);
+              cudaStream_t st, TcPartials* defer) {
+  return tc_kl_run(1, A, lda, W, ldw, H, ldh, Y, ldy, m, n, k, eps, transposed_out, ws, ws_bytes, st, defer);
 }
 
 }  // namespace dnmf

@@ -28,6 +28,7 @@
 #define DNMF_WAIT_HINT 0
 #endif
 #include "tc_common.cuh"
+#include "tc_api.cuh"
 
 namespace dnmf {
 namespace {
@@ -713,7 +714,7 @@ int64_t tc_kl_workspace_bytes(int op, int64_t m, int64_t n, int64_t k) {
 // (zero columns of W / rows of H add nothing to S = W H, and their output columns are dropped by the final reduction).
 int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* out,
               int64_t ldo, int64_t m, int64_t n, int k, float eps, int transposed_out, void* ws, int64_t ws_bytes,
-              cudaStream_t st) {
+              cudaStream_t st, TcPartials* defer) {
   if (k < 1 || k > KK) return fail(DNMF_E_UNSUPPORTED, "tcgen05 KL path: k must be in [1, %d]", KK);
   const KlPlan kp = kl_plan(mode, m, n);
   const TcPlan& pl = kp.base;
@@ -778,6 +779,10 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   };
   rc = mode == 0 ? launch(tc_kl_kernel<0>) : launch(tc_kl_kernel<1>);
   if (rc) return rc;
+  if (defer != nullptr) {      // the consumer sums the splits itself, in the same order
+    defer->P = P; defer->ldp = KK; defer->split_stride = split_stride; defer->splits = pl.splits;
+    return 0;
+  }
   int64_t so_r, so_c;
   if (mode == 0) { so_r = ldo; so_c = 1; }
   else if (transposed_out) { so_r = ldo; so_c = 1; }

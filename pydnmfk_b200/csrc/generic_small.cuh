@@ -80,11 +80,21 @@ struct RowUpdCfg {
   static constexpr int RB = raw > 64 ? 64 : (raw < 16 ? 16 : raw);   // rows per block (static smem <= 48 KB)
 };
 
+// Operand given as `splits` partial buffers `sstride` elements apart (the split-K partials an A-streaming pass leaves in
+// its workspace): the value is their sum in split order -- the order reduce_partials_kernel uses, so an update that reads
+// the partials directly is bit-identical to pass + reduction + update.  splits == 1: a plain operand.
+template <typename T>
+__device__ __forceinline__ T sum_splits(const T* __restrict__ p, int splits, int64_t sstride) {
+  T acc = p[0];
+  for (int s = 1; s < splits; ++s) acc += p[(int64_t)s * sstride];
+  return acc;
+}
+
 template <typename T, int KP, int MODE>
 __global__ void __launch_bounds__(kRowUpdThreads)
 row_update_kernel(T* __restrict__ W, int64_t ldw, const T* __restrict__ X, int64_t ldx,
                   const T* __restrict__ V, int64_t ldv, const T* __restrict__ G, int64_t m, int k, T p0,
-                  const double* __restrict__ p0_dev) {
+                  const double* __restrict__ p0_dev, int splits, int64_t sstride) {
   // p0_dev != nullptr: the scalar (BCD's Lipschitz bound) lives on the device (no host round trip, graph-capturable)
   if (p0_dev != nullptr) p0 = (T)p0_dev[0];
   constexpr int NT = kRowUpdThreads, RB = RowUpdCfg<T, KP>::RB;
@@ -109,7 +119,7 @@ row_update_kernel(T* __restrict__ W, int64_t ldw, const T* __restrict__ X, int64
       T d = T(0);
 #pragma unroll
       for (int l = 0; l < KP; ++l) d = fma(Xs[r][l], Gs[l][j], d);
-      const T v = V[row * ldv + j];
+      const T v = sum_splits(V + row * ldv + j, splits, sstride);
       T res;
       if (MODE == 0) {
         res = Xs[r][j] * (v / (d + p0));          // p0 = eps
@@ -134,7 +144,7 @@ template <typename T, int KP, int MODE>
 __global__ void __launch_bounds__(kColUpdThreads)
 col_update_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ X, int64_t ldx,
                   const T* __restrict__ Y, int64_t ysk, int64_t ysc, const T* __restrict__ G,
-                  int k, int64_t n, T p0, int clamp, const double* __restrict__ p0_dev) {
+                  int k, int64_t n, T p0, int clamp, const double* __restrict__ p0_dev, int splits, int64_t sstride) {
   if (p0_dev != nullptr) p0 = (T)p0_dev[0];
   __shared__ T Gs[KP * KP];
   const int t = threadIdx.x;
@@ -155,7 +165,7 @@ col_update_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ X, int64
         T d = T(0);
 #pragma unroll
         for (int l = 0; l < KP; ++l) d = fma(Gs[kk * KP + l], h[l], d);
-        T v = h[kk] + Y[(int64_t)kk * ysk + c * ysc] - d;
+        T v = h[kk] + sum_splits(Y + (int64_t)kk * ysk + c * ysc, splits, sstride) - d;
         h[kk] = v > p0 ? v : p0;
       }
     }
@@ -168,7 +178,7 @@ col_update_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ X, int64
       if (kk < k) {
         T d = T(0);
         T res;
-        const T y = Y[(int64_t)kk * ysk + c * ysc];
+        const T y = sum_splits(Y + (int64_t)kk * ysk + c * ysc, splits, sstride);
         if (MODE == 0) {
 #pragma unroll
           for (int l = 0; l < KP; ++l) d = fma(h[l], Gs[l * KP + kk], d);
@@ -189,23 +199,24 @@ col_update_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ X, int64
 // W(r,j) *= V(r,j) / (x[j] + eps)      (KL, W side)
 template <typename T>
 __global__ void kl_update_w_kernel(T* __restrict__ W, int64_t ldw, const T* __restrict__ V, int64_t ldv,
-                                   const T* __restrict__ x, int64_t m, int k, T eps) {
+                                   const T* __restrict__ x, int64_t m, int k, T eps, int splits, int64_t sstride) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m * k) return;
   const int64_t r = idx / k;
   const int j = (int)(idx % k);
-  W[r * ldw + j] *= V[r * ldv + j] / (x[j] + eps);
+  W[r * ldw + j] *= sum_splits(V + r * ldv + j, splits, sstride) / (x[j] + eps);
 }
 
 // H(kk,c) *= Y(kk,c) / (x[kk] + eps)   (KL, H side; optional clamp)
 template <typename T>
 __global__ void kl_update_h_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ Y, int64_t ysk,
-                                   int64_t ysc, const T* __restrict__ x, int k, int64_t n, T eps, int clamp) {
+                                   int64_t ysc, const T* __restrict__ x, int k, int64_t n, T eps, int clamp, int splits,
+                                   int64_t sstride) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)k * n) return;
   const int kk = (int)(idx / n);
   const int64_t c = idx % n;
-  T v = H[(int64_t)kk * ldh + c] * (Y[(int64_t)kk * ysk + c * ysc] / (x[kk] + eps));
+  T v = H[(int64_t)kk * ldh + c] * (sum_splits(Y + (int64_t)kk * ysk + c * ysc, splits, sstride) / (x[kk] + eps));
   if (clamp) v = v > eps ? v : eps;
   H[(int64_t)kk * ldh + c] = v;
 }

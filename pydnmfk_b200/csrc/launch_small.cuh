@@ -45,11 +45,12 @@ int gram_dispatch(const T* X, int64_t ldx, int64_t rows, int k, int trans, T* G,
 // mode 0: MU (p0 = eps), mode 1: BCD projected gradient (p0 = Lipschitz bound)
 template <typename T>
 int row_update_dispatch(int mode, T* W, int64_t ldw, const T* X, int64_t ldx, const T* V, int64_t ldv, const T* G,
-                        int64_t m, int k, T p0, const double* p0_dev, cudaStream_t st);
+                        int64_t m, int k, T p0, const double* p0_dev, cudaStream_t st, int splits = 1, int64_t sstride = 0);
 // mode 0: MU, 1: BCD, 2: HALS
 template <typename T>
 int col_update_dispatch(int mode, T* H, int64_t ldh, const T* X, int64_t ldx, const T* Y, int64_t ysk, int64_t ysc,
-                        const T* G, int k, int64_t n, T p0, int clamp, const double* p0_dev, cudaStream_t st);
+                        const T* G, int k, int64_t n, T p0, int clamp, const double* p0_dev, cudaStream_t st, int splits = 1,
+                        int64_t sstride = 0);
 template <typename T>
 int residual_dispatch(const T* A, int64_t lda, const T* W, int64_t ldw, const T* H, int64_t ldh, int64_t m,
                       int64_t n, int k, int64_t chunk, unsigned gx, unsigned gy, double* P, double* col_num,
@@ -75,13 +76,13 @@ int gram_dispatch(const T* X, int64_t ldx, int64_t rows, int k, int trans, T* G,
 
 template <typename T>
 int row_update_dispatch(int mode, T* W, int64_t ldw, const T* X, int64_t ldx, const T* V, int64_t ldv, const T* G,
-                        int64_t m, int k, T p0, const double* p0_dev, cudaStream_t st) {
+                        int64_t m, int k, T p0, const double* p0_dev, cudaStream_t st, int splits, int64_t sstride) {
   const int kp = padded_k(k);
   DNMF_DISPATCH_KP(kp, {
     constexpr int RB = RowUpdCfg<T, KP>::RB;
     const unsigned grid = (unsigned)ceil_div(m, RB);
-    if (mode == 0) row_update_kernel<T, KP, 0><<<grid, kRowUpdThreads, 0, st>>>(W, ldw, X, ldx, V, ldv, G, m, k, p0, p0_dev);
-    else row_update_kernel<T, KP, 1><<<grid, kRowUpdThreads, 0, st>>>(W, ldw, X, ldx, V, ldv, G, m, k, p0, p0_dev);
+    if (mode == 0) row_update_kernel<T, KP, 0><<<grid, kRowUpdThreads, 0, st>>>(W, ldw, X, ldx, V, ldv, G, m, k, p0, p0_dev, splits, sstride);
+    else row_update_kernel<T, KP, 1><<<grid, kRowUpdThreads, 0, st>>>(W, ldw, X, ldx, V, ldv, G, m, k, p0, p0_dev, splits, sstride);
   });
   DNMF_LAUNCH_CHECK("row_update_kernel");
   return 0;
@@ -89,13 +90,14 @@ int row_update_dispatch(int mode, T* W, int64_t ldw, const T* X, int64_t ldx, co
 
 template <typename T>
 int col_update_dispatch(int mode, T* H, int64_t ldh, const T* X, int64_t ldx, const T* Y, int64_t ysk, int64_t ysc,
-                        const T* G, int k, int64_t n, T p0, int clamp, const double* p0_dev, cudaStream_t st) {
+                        const T* G, int k, int64_t n, T p0, int clamp, const double* p0_dev, cudaStream_t st, int splits,
+                        int64_t sstride) {
   const int kp = padded_k(k);
   const unsigned grid = (unsigned)ceil_div(n, kColUpdThreads);
   DNMF_DISPATCH_KP(kp, {
-    if (mode == 0) col_update_kernel<T, KP, 0><<<grid, kColUpdThreads, 0, st>>>(H, ldh, X, ldx, Y, ysk, ysc, G, k, n, p0, clamp, p0_dev);
-    else if (mode == 1) col_update_kernel<T, KP, 1><<<grid, kColUpdThreads, 0, st>>>(H, ldh, X, ldx, Y, ysk, ysc, G, k, n, p0, clamp, p0_dev);
-    else col_update_kernel<T, KP, 2><<<grid, kColUpdThreads, 0, st>>>(H, ldh, X, ldx, Y, ysk, ysc, G, k, n, p0, clamp, p0_dev);
+    if (mode == 0) col_update_kernel<T, KP, 0><<<grid, kColUpdThreads, 0, st>>>(H, ldh, X, ldx, Y, ysk, ysc, G, k, n, p0, clamp, p0_dev, splits, sstride);
+    else if (mode == 1) col_update_kernel<T, KP, 1><<<grid, kColUpdThreads, 0, st>>>(H, ldh, X, ldx, Y, ysk, ysc, G, k, n, p0, clamp, p0_dev, splits, sstride);
+    else col_update_kernel<T, KP, 2><<<grid, kColUpdThreads, 0, st>>>(H, ldh, X, ldx, Y, ysk, ysc, G, k, n, p0, clamp, p0_dev, splits, sstride);
   });
   DNMF_LAUNCH_CHECK("col_update_kernel");
   return 0;

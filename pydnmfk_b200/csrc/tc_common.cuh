@@ -435,8 +435,9 @@ void tc_launch_split_wt(const float* W, int64_t ldw, float* Bcat, int64_t ldb, i
 // fused KL contractions (dnmf_tc_kl.cu)
 int64_t tc_kl_workspace_bytes(int op, int64_t m, int64_t n, int64_t k);
 bool tc_kl_supported(int64_t k);
+struct TcPartials;
 int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* out,
               int64_t ldo, int64_t m, int64_t n, int k, float eps, int transposed_out, void* ws, int64_t ws_bytes,
-              cudaStream_t st);
+              cudaStream_t st, TcPartials* defer = nullptr);
 
 }  // namespace dnmf

@@ -5,6 +5,9 @@ the process groups).  Every numeric operation of the update loop is one of the
 hand-written kernels behind the C-ABI (include/dnmf.h); there is no CPU or
 eager-PyTorch fallback -- calling this layer without a CUDA device raises.
 """
+import ctypes as C
+import os
+
 import numpy as np
 import torch
 
@@ -18,8 +21,14 @@ def require_cuda():
         raise RuntimeError('pydnmfk_b200 needs a CUDA device (sm_100a); it has no CPU fallback')
 
 
-def to_device(x, dtype=None, device=None):
-    """numpy / torch (host or device) -> contiguous CUDA tensor."""
+def fused_epilogue_enabled():
+    """DNMF_FUSED_EPILOGUE=0 keeps pass, split reduction and update as separate launches (A/B runs)."""
+    return os.environ.get('DNMF_FUSED_EPILOGUE', '1') != '0'
+
+
+def to_device(x, dtype=None, device=None, non_blocking=False):
+    """numpy / torch (host or device) -> contiguous CUDA tensor.  ``non_blocking``: a page-locked host source is copied
+    asynchronously on the current stream (the caller synchronises before the host buffer may change)."""
     require_cuda()
     if device is None:
         device = torch.device('cuda', torch.cuda.current_device())
@@ -34,7 +43,7 @@ def to_device(x, dtype=None, device=None):
         t = torch.from_numpy(a)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
-    t = t.to(device, non_blocking=False)
+    t = t.to(device, non_blocking=bool(non_blocking) and (not t.is_cuda) and t.is_pinned())
     return t.contiguous()
 
 
@@ -167,6 +176,67 @@ class DeviceOps:
                self._stream())
         self._t1(ev)
         return Y
+
+    # ---- pass with the split reduction deferred to the consumer (include/dnmf.h: dnmf_*_p) ---------------------------
+    def _pass_partials(self, name, timer, op, A, k, *args):
+        """Run a `_p` pass; returns the int64[4] view (host array kept alive by the caller) or None when the call is
+        not served by the tcgen05 path (the caller then uses the plain op)."""
+        if not fused_epilogue_enabled() or A.dtype != torch.float32:
+            return None
+        m, n = A.shape
+        dt = _DT[A.dtype]
+        ws, wsb = self._ws_for(op, m, n, k, dt)
+        view = (C.c_int64 * 4)()
+        ev = self._t0(timer)
+        rc = getattr(L.raw(), name)(*args, dt, self.math_mode, ws, wsb, view, self._stream())
+        if rc == L.E_UNSUPPORTED:
+            if ev is not None:
+                self.timers[timer].pop()
+            return None
+        if rc != 0:
+            raise L.DnmfError(name, rc, L.raw().dnmf_last_error().decode())
+        self._t1(ev)
+        return view
+
+    def ah_p(self, A, H):
+        m, n = A.shape
+        k = H.shape[0]
+        return self._pass_partials('dnmf_ah_p', 'ah', L.OP_AH, A, k, A.data_ptr(), _ld(A), H.data_ptr(), _ld(H), m, n, k)
+
+    def wta_p(self, A, W):
+        m, n = A.shape
+        k = W.shape[1]
+        return self._pass_partials('dnmf_wta_p', 'wta', L.OP_WTA, A, k, A.data_ptr(), _ld(A), W.data_ptr(), _ld(W), m, n, k)
+
+    def kl_uht_p(self, A, W, H, eps):
+        m, n = A.shape
+        k = W.shape[1]
+        return self._pass_partials('dnmf_kl_uht_p', 'kl_uht', L.OP_KL_UHT, A, k, A.data_ptr(), _ld(A), W.data_ptr(), _ld(W),
+                                   H.data_ptr(), _ld(H), m, n, k, float(eps))
+
+    def kl_wtu_p(self, A, W, H, eps):
+        m, n = A.shape
+        k = W.shape[1]
+        return self._pass_partials('dnmf_kl_wtu_p', 'kl_wtu', L.OP_KL_WTU, A, k, A.data_ptr(), _ld(A), W.data_ptr(), _ld(W),
+                                   H.data_ptr(), _ld(H), m, n, k, float(eps))
+
+    def mu_update_w_p(self, W, view, G, eps):
+        m, k = W.shape
+        L.call('dnmf_mu_update_w_p', W.data_ptr(), _ld(W), view, G.data_ptr(), m, k, float(eps), _DT[W.dtype], self._stream())
+
+    def mu_update_h_p(self, H, view, G, eps, clamp=False):
+        k, n = H.shape
+        L.call('dnmf_mu_update_h_p', H.data_ptr(), _ld(H), view, G.data_ptr(), k, n, float(eps), 1 if clamp else 0,
+               _DT[H.dtype], self._stream())
+
+    def kl_update_w_p(self, W, view, x, eps):
+        m, k = W.shape
+        L.call('dnmf_kl_update_w_p', W.data_ptr(), _ld(W), view, x.data_ptr(), m, k, float(eps), _DT[W.dtype], self._stream())
+
+    def kl_update_h_p(self, H, view, x, eps, clamp=False):
+        k, n = H.shape
+        L.call('dnmf_kl_update_h_p', H.data_ptr(), _ld(H), view, x.data_ptr(), k, n, float(eps), 1 if clamp else 0,
+               _DT[H.dtype], self._stream())
 
     def gram(self, X, trans):
         """trans=False: X.T @ X for X [rows x k];  trans=True: X @ X.T for X [k x rows]."""

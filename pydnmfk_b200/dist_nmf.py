@@ -458,6 +458,12 @@ class nmf_algorithms_1D(_AlgBase):
     def Fro_MU_update_W(self):
         """dist_nmf.py:715-732."""
         HH_T = self._gram_H(self.H_j)
+        if self.p_c == 1 and self._mon is None:
+            # pass + ONE epilogue launch: the update sums the pass's split partials itself (dnmf_ah_p / dnmf_mu_update_w_p)
+            view = self.ops.ah_p(self.A_ij, self.H_j)
+            if view is not None:
+                self.ops.mu_update_w_p(self.W_i, view, HH_T, self.eps)
+                return
         AH = self._AH(self.H_j)
         self._monitor_sample(self.W_i, AH, HH_T)
         self.ops.mu_update_w(self.W_i, AH, HH_T, self.eps)
@@ -467,11 +473,20 @@ class nmf_algorithms_1D(_AlgBase):
         """dist_nmf.py:735-751."""
         if self._px is not None:
             G = self.ops.gram(self.W_i, trans=False)                      # this rank's W_i^T W_i
+            view = self.ops.wta_p(self.A_ij, self.W_i)
+            if view is not None:                                          # the push kernel sums the split partials itself
+                self._px.update_h_p(0, self.H_j, view, G, self.eps)
+                return
             Yt = self.ops.wta(self.A_ij, self.W_i, transposed_out=True)   # this rank's (W_i^T A_i)^T
             self._px.update_h(0, self.H_j, Yt, G, self.eps)
             return
         W_TW = self._gram_W(self.W_i)
         self._monitor_keep(W_TW)
+        if self.p_r == 1 and self._mon is None:
+            view = self.ops.wta_p(self.A_ij, self.W_i)
+            if view is not None:
+                self.ops.mu_update_h_p(self.H_j, view, W_TW, self.eps)
+                return
         AtW, _ = self._WTA(self.W_i)
         self.ops.mu_update_h(self.H_j, AtW, W_TW, self.eps)
 
@@ -503,6 +518,11 @@ class nmf_algorithms_1D(_AlgBase):
     def KL_MU_update_W(self):
         """dist_nmf.py:813-830."""
         x2 = self.sum_along_axis(self.H_j, p=self.p_c, axis=1)
+        if self.p_c == 1:
+            view = self.ops.kl_uht_p(self.A_ij, self.W_i, self.H_j, self.eps)
+            if view is not None:
+                self.ops.kl_update_w_p(self.W_i, view, x2, self.eps)
+                return
         sk = self.glob_UX(axis=0)
         self.ops.kl_update_w(self.W_i, sk, x2, self.eps)
 
@@ -510,10 +530,19 @@ class nmf_algorithms_1D(_AlgBase):
         """dist_nmf.py:832-849."""
         if self._px is not None:
             x = self.ops.colsum(self.W_i)                                  # this rank's column sums of W_i
+            view = self.ops.kl_wtu_p(self.A_ij, self.W_i, self.H_j, self.eps)
+            if view is not None:
+                self._px.update_h_p(3, self.H_j, view, x, self.eps)
+                return
             Yt = self.ops.kl_wtu(self.A_ij, self.W_i, self.H_j, self.eps, transposed_out=True)
             self._px.update_h(3, self.H_j, Yt, x, self.eps)
             return
         x2 = self.sum_along_axis(self.W_i, p=self.p_r, axis=0)
+        if self.p_r == 1:
+            view = self.ops.kl_wtu_p(self.A_ij, self.W_i, self.H_j, self.eps)
+            if view is not None:
+                self.ops.kl_update_h_p(self.H_j, view, x2, self.eps)
+                return
         sk = self.glob_UX(axis=1)
         self.ops.kl_update_h(self.H_j, sk, x2, self.eps)
 
@@ -543,6 +572,10 @@ class nmf_algorithms_1D(_AlgBase):
         """dist_nmf.py:895-913."""
         if self._px is not None:
             G = self.ops.gram(self.W_i, trans=False)
+            view = self.ops.wta_p(self.A_ij, self.W_i)
+            if view is not None:
+                self._px.update_h_p(2, self.H_j, view, G, self.eps)
+                return
             Yt = self.ops.wta(self.A_ij, self.W_i, transposed_out=True)
             self._px.update_h(2, self.H_j, Yt, G, self.eps)
             return

@@ -70,6 +70,13 @@ class PeerExchange:
                Yt.stride(0), aux.data_ptr(), n, k, float(eps), 1 if clamp else 0, self.dt,
                torch.cuda.current_stream().cuda_stream)
 
+    def update_h_p(self, mode, H, view, aux, eps, clamp=False):
+        """update_h with this rank's partial given as the split-K partial view of `DeviceOps.wta_p / kl_wtu_p`."""
+        k, n = H.shape
+        assert (k, n) == (self.k, self.n) and H.dtype == self.tdtype and H.stride(1) == 1 and aux.is_contiguous()
+        L.call('dnmf_xchg_update_h_p', self._bases, self.P, self.me, int(mode), H.data_ptr(), H.stride(0), view,
+               aux.data_ptr(), n, k, float(eps), 1 if clamp else 0, self.dt, torch.cuda.current_stream().cuda_stream)
+
     def check(self):
         """Raise if a wait for a peer timed out (the peer died or never launched its half of an exchange)."""
         err = C.c_int(0)

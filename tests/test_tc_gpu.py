@@ -191,3 +191,52 @@ def test_residual_on_the_tensor_pipeline(ops):
     f = np.float64
     rr = np.linalg.norm(A.astype(f) - W.astype(f) @ H.astype(f)) ** 2
     assert abs(got[0] - rr) <= 2e-6 * rr and abs(got[0] - ref[0]) <= 2e-6 * rr and abs(got[1] - ref[1]) <= 1e-6 * ref[1]
+
+
+@pytest.mark.parametrize('m,n,k', [(2048, 2048, 32), (1000, 1000, 32), (515, 2052, 20), (4100, 300, 64), (8192, 1024, 10),
+                                   (1024, 8192, 32)])
+def test_fused_epilogue_is_bit_identical(ops, m, n, k):
+    """dnmf_*_p + dnmf_*_update_*_p (the update sums the pass's split partials itself) must give exactly the factors of
+    pass -> reduce_partials -> update, for the FRO and (k <= 32) KL half-steps."""
+    rs = np.random.RandomState(7)
+    A, W, H = (_dev(rs.rand(*s).astype(np.float32)) for s in ((m, n), (m, k), (k, n)))
+    eps = 1.1920929e-07
+    G_h = ops.gram(H, trans=True)
+    G_w = ops.gram(W, trans=False)
+    # FRO W
+    W1 = W.clone(); ops.mu_update_w(W1, ops.ah(A, H), G_h, eps)
+    view = ops.ah_p(A, H); assert view is not None and view[2] >= 1
+    W2 = W.clone(); ops.mu_update_w_p(W2, view, G_h, eps)
+    assert torch.equal(W1, W2)
+    # FRO H
+    H1 = H.clone(); ops.mu_update_h(H1, ops.wta(A, W, transposed_out=True), G_w, eps, y_transposed=True)
+    view = ops.wta_p(A, W); assert view is not None
+    H2 = H.clone(); ops.mu_update_h_p(H2, view, G_w, eps)
+    assert torch.equal(H1, H2)
+    H3 = H.clone(); ops.mu_update_h(H3, ops.wta(A, W), G_w, eps)          # and the non-transposed plain form
+    assert torch.equal(H1, H3)
+    if k <= 32:
+        x2, x1 = ops.rowsum(H), ops.colsum(W)
+        W1 = W.clone(); ops.kl_update_w(W1, ops.kl_uht(A, W, H, eps), x2, eps)
+        view = ops.kl_uht_p(A, W, H, eps); assert view is not None
+        W2 = W.clone(); ops.kl_update_w_p(W2, view, x2, eps)
+        assert torch.equal(W1, W2)
+        H1 = H.clone(); ops.kl_update_h(H1, ops.kl_wtu(A, W, H, eps, transposed_out=True), x1, eps, y_transposed=True)
+        view = ops.kl_wtu_p(A, W, H, eps); assert view is not None
+        H2 = H.clone(); ops.kl_update_h_p(H2, view, x1, eps)
+        assert torch.equal(H1, H2)
+    else:
+        assert ops.kl_uht_p(A, W, H, eps) is None         # not on the tcgen05 path: the caller falls back
+
+
+def test_fused_epilogue_falls_back(ops):
+    """fp64 and forced-generic calls are not served by the _p passes."""
+    from pydnmfk_b200 import _lib as L
+    A = torch.rand((512, 512), device='cuda', dtype=torch.float64)
+    H = torch.rand((8, 512), device='cuda', dtype=torch.float64)
+    assert ops.ah_p(A, H) is None
+    L.set_force_generic(True)
+    try:
+        assert ops.ah_p(A.float(), H.float()) is None
+    finally:
+        L.set_force_generic(False)
