@@ -609,7 +609,20 @@ def run_ours(args):
             traffic = cap['kernels'][dom[0]]['dram_bytes_per_launch']
     except Exception:
         pass
-    roofline = {'bound': 'hbm', 'achieved': dom[2] if dom else None, 'peak': peak, 'unit': 'GB/s',
+    # tensor-pipe side of the same kernel: 3 tf32 terms per product (fp32-accurate split), 2 GEMMs per pass for KL.
+    # Peak = half the measured bf16 throughput (kind::tf32 runs at half the bf16 rate); nominal dense tf32 = 1125 TF/s.
+    tensor = None
+    if dom:
+        kp = 16 if k <= 16 else (32 if k <= 32 else 64)
+        gemms = 2 if dom[0].split(':')[-1].startswith('kl') or dom[0].endswith('ah_res') else 1
+        flops = 2.0 * float(m_i) * n_j * kp * 3 * gemms
+        t_ms = per_kernel[dom[0]]['mean_ms']
+        tf32_peak = float(peaks.get('bf16_tflops_sustained', 1380.0)) / 2.0
+        ach = flops / (t_ms * 1e-3) / 1e12
+        tensor = {'tf32_flops_per_launch': flops, 'achieved_tflops': ach, 'peak_tflops': tf32_peak,
+                  'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained / 2' if 'bf16_tflops_sustained' in peaks else 'fallback 690 TF/s',
+                  'frac': ach / tf32_peak, 'frac_of_nominal_1125': ach / 1125.0}
+    roofline = {'bound': 'hbm', 'achieved': dom[2] if dom else None, 'peak': peak, 'unit': 'GB/s', 'tensor': tensor,
                 'frac': (dom[2] / peak) if dom else None, 'traffic': traffic,
                 'traffic_source': 'profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)' if traffic else None, 'kernel': dom[0] if dom else None,
                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': pass_bytes, 'per_kernel': per_kernel,

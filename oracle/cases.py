@@ -118,6 +118,12 @@ def _grid_cases():
             c = _case('u2048k16_%dx%d_fro_%s_i10' % (g + (method,)), 2048, 2048, 16, g, 'fro', method, 10, reseed=7)
             c['expect_tc'] = True
             cs.append(c)
+    # BCD beyond 10 iterations in fp32: 100 accept / restore decisions on the device-resident control state
+    cs.append(_case('u64x48k4_1x1_fro_bcd_i100_32', 64, 48, 4, (1, 1), 'fro', 'bcd', 100, reseed=7))
+    cs.append(_case('u64x48k4_2x1_fro_bcd_i100_32', 64, 48, 4, (2, 1), 'fro', 'bcd', 100, reseed=7))
+    c = _case('u2048k16_1x1_fro_bcd_i100', 2048, 2048, 16, (1, 1), 'fro', 'bcd', 100, reseed=7)
+    c['expect_tc'] = True
+    cs.append(c)
     # prune path: exact-zero rows/cols, fp32 in -> float64 out (utils.py:195,198)
     for g in ((1, 1), (2, 1), (1, 2), (2, 2)):
         for norm in ('fro', 'kl'):
