@@ -303,7 +303,7 @@ int dnmf_ah_residual(const void* A, int64_t lda, const void* W, int64_t ldw, con
  * the same order: bit-identical results, one launch and one factor-sized HBM round trip less per half-step
  * (dist_nmf.py:730-732, :749-751, :806-830, :808-849 as pass + update = 2 launches).
  * The pass variants return DNMF_E_UNSUPPORTED, without side effects, when the call is not served by the tcgen05 path
- * (fp64, small or unaligned shards, KL with k > 32): the caller then uses the plain entry points.  fp32 only.
+ * (fp64, small or unaligned shards): the caller then uses the plain entry points.  fp32 only.
  * The view is valid until the next call that uses the same workspace. */
 int dnmf_ah_p(const void* A, int64_t lda, const void* H, int64_t ldh, int64_t m, int64_t n, int64_t k, int dtype,
               int math_mode, void* ws, int64_t ws_bytes, int64_t* view4, void* stream);

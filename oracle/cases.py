@@ -107,6 +107,9 @@ def _grid_cases():
         ('u2048', 2048, 2048, (2, 2), 'fro', 64, 10),
         ('u4096x1024', 4096, 1024, (1, 1), 'fro', 32, 10), ('u4096x1024', 4096, 1024, (2, 1), 'kl', 32, 100),
         ('u4096x1024', 4096, 1024, (2, 2), 'fro', 64, 100), ('u4096x1024', 4096, 1024, (1, 1), 'kl', 10, 100),
+        # KL with 32 < k <= 64: the 64-wide build of the fused tcgen05 kernel (dnmf_tc_kl64.cu)
+        ('u2048', 2048, 2048, (1, 1), 'kl', 64, 10), ('u2048', 2048, 2048, (2, 1), 'kl', 48, 10),
+        ('u4096x1024', 4096, 1024, (1, 1), 'kl', 64, 100),
     ]
     for tag, m, n, g, norm, k, itr in big:
         c = _case('%sk%d_%dx%d_%s_mu_i%d' % (tag, k, g[0], g[1], norm, itr), m, n, k, g, norm, 'mu', itr, reseed=7)

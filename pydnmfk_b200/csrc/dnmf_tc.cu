@@ -625,7 +625,7 @@ bool tc_eligible(int op, const void* A, int64_t lda, int64_t m, int64_t n, int64
   if (tls().force_generic) return false;
   const bool kl = (op == DNMF_OP_KL_UHT || op == DNMF_OP_KL_WTU);
   if (op != DNMF_OP_AH && op != DNMF_OP_WTA && !kl) return false;
-  if (kl && !tc_kl_supported(k)) return false;
+  if (kl && !tc_kl_supported(k) && !tc_kl_supported_k64(k)) return false;
   if (dtype != DNMF_F32) return false;
   if (k < 1 || k > 64) return false;
   if (((uintptr_t)A % 16) != 0 || (lda % 4) != 0) return false;
@@ -648,6 +648,7 @@ int64_t tc_workspace_bytes(int op, int64_t m, int64_t n, int64_t k, int dtype) {
   if (op == DNMF_OP_AH) { const TcPlan p = tc_plan(m, n, tc_padded_k((int)k)); return p.bcat_bytes + p.partial_bytes; }
   if (op == DNMF_OP_WTA) { const TcPlan p = tc_plan(n, m, tc_padded_k((int)k)); return p.bcat_bytes + p.partial_bytes; }
   if ((op == DNMF_OP_KL_UHT || op == DNMF_OP_KL_WTU) && tc_kl_supported(k)) return tc_kl_workspace_bytes(op, m, n, k);
+  if ((op == DNMF_OP_KL_UHT || op == DNMF_OP_KL_WTU) && tc_kl_supported_k64(k)) return tc_kl_workspace_bytes_k64(op, m, n, k);
   return 0;
 }
 
@@ -664,11 +665,13 @@ int tc_wta(const float* A, int64_t lda, const float* W, int64_t ldw, float* Y, i
 int tc_kl_uht(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* V, int64_t ldv,
               int64_t m, int64_t n, int k, float eps, int math_mode, void* ws, int64_t ws_bytes, cudaStream_t st,
               TcPartials* defer) {
+  if (k > 32) return tc_kl_run_k64(0, A, lda, W, ldw, H, ldh, V, ldv, m, n, k, eps, 0, ws, ws_bytes, st, defer);
   return tc_kl_run(0, A, lda, W, ldw, H, ldh, V, ldv, m, n, k, eps, 0, ws, ws_bytes, st, defer);
 }
 int tc_kl_wtu(const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* Y, int64_t ldy,
               int64_t m, int64_t n, int k, float eps, int transposed_out, int math_mode, void* ws, int64_t ws_bytes,
               cudaStream_t st, TcPartials* defer) {
+  if (k > 32) return tc_kl_run_k64(1, A, lda, W, ldw, H, ldh, Y, ldy, m, n, k, eps, transposed_out, ws, ws_bytes, st, defer);
   return tc_kl_run(1, A, lda, W, ldw, H, ldh, Y, ldy, m, n, k, eps, transposed_out, ws, ws_bytes, st, defer);
 }
 

@@ -33,11 +33,27 @@
 namespace dnmf {
 namespace {
 
-constexpr int KK = 32;            // factor width handled by this kernel
+// KL_KK: factor width this translation unit is built for.  32 (default: any k <= 32, zero-padded) or 64 (32 < k <= 64,
+// dnmf_tc_kl64.cu includes this file with KL_KK = 64: two splitter groups, single-buffered accumulator, see KlCfg).
+#ifndef KL_KK
+#define KL_KK 32
+#endif
+constexpr int KK = KL_KK;         // factor width handled by this kernel
+constexpr int KATOMS = KK / 32;   // 128-byte swizzle atoms along k of one factor-tile row
+static_assert(KK == 32 || KK == 64, "KL_KK must be 32 or 64");
+#if KL_KK == 64
+#define KL_FN(name) name##_k64
+#else
+#define KL_FN(name) name
+#endif
 // KL_GROUPS splitter groups of 4 warps work on tiles round-robin; the per-tile chain (A tile -> S load -> divide -> split ->
 // tensor-memory store -> GEMM2 -> slot free) is latency-bound, so the number of tiles in flight sets the pass time.
 #ifndef KL_GROUPS
+#if KL_KK == 64
+#define KL_GROUPS 2       // tensor memory: 128 (accumulator) + 2 x 64 (U ring) + 2 x 64 (S pair ring) + 128 (Fx) = 512 columns
+#else
 #define KL_GROUPS 3       // round 2: 3 groups are 10-17 % faster than 2 (profiles/r02_kl_lab.md)
+#endif
 #endif
 constexpr int KL_THREADS = 512 + 128 * (KL_GROUPS - 2);
 // Warp-role placement.  The SM's issue arbiter prefers the higher warp id, and setmaxnreg moves registers per warpgroup:
@@ -83,10 +99,16 @@ struct KlCfg {
 #else
   static constexpr int F_ROWS = TC_BK;
 #endif
-  static constexpr int F_BYTES = 2 * F_ROWS * KK * 4;  // FrCat tile [hi F_ROWS r | lo F_ROWS r][k]: 8 KB, 16 KB for pairs
+  static constexpr int F_ATOM_BYTES = F_ROWS * 128;    // F_ROWS rows of one 128-byte swizzle atom (32 factor columns)
+  static constexpr int F_BYTES = 2 * KATOMS * F_ATOM_BYTES;   // FrCat tile [hi: KATOMS atoms | lo: KATOMS atoms]: 8 / 16 / 32 KB
 #ifndef KL_SA
+#if KL_KK == 64
+#define KL_SA 5           // 80 KB A ring + 3 x 16 KB Bcat + 2 x 32 KB FrCat pairs = 192 KB
+#define KL_SB 3
+#else
 #define KL_SA 8
 #define KL_SB 4
+#endif
 #if KL_S1 == 2
 #define KL_SF 2
 #else
@@ -94,10 +116,12 @@ struct KlCfg {
 #endif
 #endif
   static constexpr int SA = KL_SA, SB = KL_SB, SF = KL_SF;
-#if KL_S1 == 2
-  static constexpr int NBUF = 2, NT = 3, NS = 2, S_COLS = 2 * KK;       // one S slot = the S tiles of a pair
+#if KL_S1 == 2 && KL_KK == 64
+  static constexpr int NBUF = 1, NT = 2, NS = 2, S_COLS = 64;
+#elif KL_S1 == 2
+  static constexpr int NBUF = 2, NT = 3, NS = 2, S_COLS = 64;           // one S slot = the S tiles of a pair
 #elif KL_S1
-  static constexpr int NBUF = 2, NT = 3, NS = 4, S_COLS = KK;
+  static constexpr int NBUF = 2, NT = 3, NS = 4, S_COLS = 32;
 #else
 #ifndef KL_NT
 #if KL_GROUPS == 3
@@ -110,13 +134,14 @@ struct KlCfg {
 #define KL_NS 3
 #endif
 #endif
-  static constexpr int NBUF = KL_NBUF, NT = KL_NT, NS = KL_NS, S_COLS = 2 * KK;
+  static constexpr int NBUF = KL_NBUF, NT = KL_NT, NS = KL_NS, S_COLS = 64;
 #endif
   static constexpr int ACC_COL0 = 0;
   static constexpr int OP_COL0 = NBUF * N2;            // 128
   static constexpr int S_COL0 = OP_COL0 + NT * 64;
-  static constexpr int FX_COL0 = S_COL0 + NS * S_COLS; // 448
-  static_assert(FX_COL0 + 64 <= 512, "TMEM has 512 columns");
+  static constexpr int FX_COL0 = S_COL0 + NS * S_COLS; // 448 (384 for KK = 64)
+  static_assert(FX_COL0 + 2 * KK <= 512, "TMEM has 512 columns");
+  static_assert(KK == 32 || KL_S1 == 2, "the 64-wide build needs the paired S tiles");
   // A splitter group waits on a ring slot by phase PARITY, which is only unambiguous while the slot's previous use has
   // completed.  The group knows that for every tile up to its own previous one (tile - KL_GROUPS; GEMM1 and GEMM2 complete
   // in tile order), and the slot's previous use is tile - NS (resp. tile - NT): both rings need at least KL_GROUPS slots,
@@ -268,8 +293,12 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(bar(iFE + s), ph ^ 1u);
           if (dbg & 0x20000) { mbar_arrive(bar(iFF + s)); if (++s == SF) { s = 0; ph ^= 1u; } continue; }   // ablation
           mbar_expect_tx(bar(iFF + s), Cfg::F_BYTES);
-          tma_load_2d(sF0 + s * Cfg::F_BYTES, &tmF, bar(iFF + s), 0, kt * TC_BK);
-          tma_load_2d(sF0 + s * Cfg::F_BYTES + Cfg::F_BYTES / 2, &tmF, bar(iFF + s), 0, (int)fr_rows_pad + kt * TC_BK);
+#pragma unroll
+          for (int a = 0; a < KATOMS; ++a) {      // one TMA box per 128-byte swizzle atom along k
+            tma_load_2d(sF0 + s * Cfg::F_BYTES + a * Cfg::F_ATOM_BYTES, &tmF, bar(iFF + s), a * 32, kt * TC_BK);
+            tma_load_2d(sF0 + s * Cfg::F_BYTES + Cfg::F_BYTES / 2 + a * Cfg::F_ATOM_BYTES, &tmF, bar(iFF + s), a * 32,
+                        (int)fr_rows_pad + kt * TC_BK);
+          }
           if (++s == SF) { s = 0; ph ^= 1u; }
         }
       }
@@ -280,7 +309,8 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     //   else : cols [0,32) Fx_hi*Fr_hi ; cols [32,64) Fx_hi*Fr_lo + Fx_lo*Fr_hi
     constexpr uint32_t idesc_full = make_idesc(N2, 0);
     constexpr uint32_t idesc_half = make_idesc(KK, 0);
-    (void)idesc_full;
+    constexpr uint32_t idesc_pair = make_idesc(64, 0);      // GEMM1 on a tile pair: N = 64 reduced indices
+    (void)idesc_full; (void)idesc_half; (void)idesc_pair;
     int sf = 0, ss = 0;
     uint32_t pf = 0, ps = 0, pxu = 0;
     const uint32_t fx_tmem = tmem_base + (uint32_t)Cfg::FX_COL0;
@@ -299,10 +329,14 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (dbg & 4)
           umma_commits_only(bar(iSF + ss), bar(iFE + sf), bar(iXE), (j + JSTEP >= ntiles) ? 1u : 0u);
         else
-#if KL_S1 == 2
-          umma_tile_cat<2 * KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS), fx_tmem,
-                                make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), idesc_full,
-                                bar(iSF + ss), bar(iFE + sf), bar(iXE), (j + JSTEP >= ntiles) ? 1u : 0u);
+#if KL_S1 == 2 && KL_KK == 64
+          umma_tile_cat64(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS), fx_tmem,
+                          make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), idesc_pair,
+                          bar(iSF + ss), bar(iFE + sf), bar(iXE), (j + JSTEP >= ntiles) ? 1u : 0u);
+#elif KL_S1 == 2
+          umma_tile_cat<64>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS), fx_tmem,
+                            make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), idesc_pair,
+                            bar(iSF + ss), bar(iFE + sf), bar(iXE), (j + JSTEP >= ntiles) ? 1u : 0u);
 #elif KL_S1
           umma_tile_cat<KK>(tmem_base + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS), fx_tmem,
                             make_smem_desc(sF0 + sf * Cfg::F_BYTES, 16, 1024), idesc_half,
@@ -383,18 +417,21 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(bar(iXE), pxe ^ 1u);              // the previous unit's GEMM1s have finished reading Fx
         tc_fence_after();
         const int64_t x = (int64_t)xb * TC_BM + r;
-        uint32_t hi[KK], lo[KK];
         const float* frow = Fx + x * ldfx;
-#pragma unroll
-        for (int j = 0; j < KK; ++j) {
-          const float w = (x < x_len && j < k_real) ? frow[j] : 0.f;      // factor columns beyond k: zero padding
-          const float h = tf32_hi(w, 1);
-          hi[j] = __float_as_uint(h);
-          lo[j] = __float_as_uint(tf32_round_up(w - h));
-        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::FX_COL0;
-        tmem_st_x32(taddr, hi);
-        tmem_st_x32(taddr + 32, lo);
+#pragma unroll
+        for (int c0 = 0; c0 < KK; c0 += 32) {       // hi columns [0, KK), lo columns [KK, 2 KK), 32 at a time
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float w = (x < x_len && c0 + j < k_real) ? frow[c0 + j] : 0.f;      // factor columns beyond k: zero padding
+            const float h = tf32_hi(w, 1);
+            hi[j] = __float_as_uint(h);
+            lo[j] = __float_as_uint(tf32_round_up(w - h));
+          }
+          tmem_st_x32(taddr + c0, hi);
+          tmem_st_x32(taddr + KK + c0, lo);
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -455,7 +492,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (q == 0 && lane == 0 && !(dbg & 4)) mbar_arrive(bar(iFE + tile % SF));
 #endif
         tc_fence_after();
-        const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS + s_half * KK);
+        const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::S_COL0 + ss * Cfg::S_COLS + s_half * 32);
         {
 #if KL_S1
           uint32_t s0[32];
@@ -607,15 +644,19 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(bar(iCF + buf), accphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COL0 + buf * N2);
-        uint32_t a[KK], b[KK];
+        constexpr int DCH = (KK > 32) ? 16 : KK;      // columns folded per batch of loads (register budget at KK = 64)
 #pragma unroll
-        for (int j0 = 0; j0 < KK; j0 += 16) {
-          tmem_ld_x16(taddr + j0, *reinterpret_cast<uint32_t(*)[16]>(&a[j0]));
-          tmem_ld_x16(taddr + KK + j0, *reinterpret_cast<uint32_t(*)[16]>(&b[j0]));
+        for (int h0 = 0; h0 < KK; h0 += DCH) {
+          uint32_t a[DCH], b[DCH];
+#pragma unroll
+          for (int j0 = 0; j0 < DCH; j0 += 16) {
+            tmem_ld_x16(taddr + h0 + j0, *reinterpret_cast<uint32_t(*)[16]>(&a[j0]));
+            tmem_ld_x16(taddr + KK + h0 + j0, *reinterpret_cast<uint32_t(*)[16]>(&b[j0]));
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < DCH; ++j) acc[h0 + j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
         }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < KK; ++j) acc[j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iCE + buf));
@@ -644,7 +685,7 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 template <bool TRANS>
 __global__ void __launch_bounds__(256) kl_split_fr_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ FrCat,
                                                           int64_t r_len, int64_t r_pad, int k) {
-  __shared__ float tile[64][33];
+  __shared__ float tile[64][KK + 1];
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   if (TRANS) {
     for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
@@ -673,7 +714,7 @@ __global__ void __launch_bounds__(256) kl_split_fr_kernel(const float* __restric
 // Ht[c][j] = H[j][c] for j < k, 0 for k <= j < KK
 __global__ void __launch_bounds__(256) kl_transpose_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Ht,
                                                            int64_t n, int k) {
-  __shared__ float tile[64][33];
+  __shared__ float tile[64][KK + 1];
   const int64_t c0 = (int64_t)blockIdx.x * 64;
   for (int idx = threadIdx.x; idx < 64 * k; idx += 256) {
     const int j = idx / 64, c = idx % 64;
@@ -703,18 +744,18 @@ KlPlan kl_plan(int mode, int64_t m, int64_t n) {       // every size is for the 
 
 }  // namespace
 
-bool tc_kl_supported(int64_t k) { return k >= 1 && k <= KK; }
+bool KL_FN(tc_kl_supported)(int64_t k) { return k >= 1 && k <= KK; }
 
-int64_t tc_kl_workspace_bytes(int op, int64_t m, int64_t n, int64_t k) {
+int64_t KL_FN(tc_kl_workspace_bytes)(int op, int64_t m, int64_t n, int64_t k) {
   const KlPlan p = kl_plan(op == DNMF_OP_KL_UHT ? 0 : 1, m, n);
   return p.base.bcat_bytes + p.frcat_bytes + p.ht_bytes + p.base.partial_bytes;
 }
 
 // ws = [Bcat | FrCat | Ht | partials].  The kernel is written for KK = 32 factor columns; smaller k ride along zero-padded
 // (zero columns of W / rows of H add nothing to S = W H, and their output columns are dropped by the final reduction).
-int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* out,
-              int64_t ldo, int64_t m, int64_t n, int k, float eps, int transposed_out, void* ws, int64_t ws_bytes,
-              cudaStream_t st, TcPartials* defer) {
+int KL_FN(tc_kl_run)(int mode, const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* out,
+                     int64_t ldo, int64_t m, int64_t n, int k, float eps, int transposed_out, void* ws, int64_t ws_bytes,
+                     cudaStream_t st, TcPartials* defer) {
   if (k < 1 || k > KK) return fail(DNMF_E_UNSUPPORTED, "tcgen05 KL path: k must be in [1, %d]", KK);
   const KlPlan kp = kl_plan(mode, m, n);
   const TcPlan& pl = kp.base;
@@ -759,7 +800,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   if (rc) return rc;
   rc = tc_make_map(&tmB, Bcat, 2 * KK, r_len, pl.ldb, TC_BK, 2 * KK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, 32, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const int64_t split_stride = x_len * KK;
   // (for UHT the x-side factor rows are read straight from W with its own leading dimension: only k_real columns exist)
@@ -793,6 +834,7 @@ int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw
   return 0;
 }
 
+#if KL_KK == 32      // the residual variants (BCD, k <= 32) exist in the 32-wide build only
 // ---- V = A H^T together with ||A - W H||^2 and ||A||^2 in ONE pass over A (MODE 3) -------------------------------------
 // ws = [Bcat | FrCat | partials | pairs (grid x 256 x 2 float64)]
 int64_t tc_ah_residual_workspace_bytes(int64_t m, int64_t n) {
@@ -827,7 +869,7 @@ int tc_ah_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw,
   if (rc) return rc;
   rc = tc_make_map(&tmB, Bcat, 2 * KK, n, pl.ldb, TC_BK, 2 * KK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, 32, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   auto kern = tc_kl_kernel<3>;
   static bool attr_set = false;
@@ -881,7 +923,7 @@ int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, co
   alignas(64) CUtensorMap tmA, tmF;
   int rc = tc_make_map(&tmA, A, m, n, lda, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, KK, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = tc_make_map(&tmF, FrCat, 2 * kp.r_pad, KK, KK, 32, KlCfg::F_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   auto kern = tc_kl_kernel<2>;
   static bool attr_set = false;
@@ -899,5 +941,7 @@ int tc_residual_run(const float* A, int64_t lda, const float* W, int64_t ldw, co
   *n_pairs = (int64_t)pl.grid * KL_PAIRS;
   return 0;
 }
+
+#endif  // KL_KK == 32
 
 }  // namespace dnmf

@@ -275,6 +275,85 @@ __device__ __forceinline__ void umma_tile_cat(uint32_t d_tmem, uint32_t a_hi, ui
       : "memory");
 }
 
+// One PAIR of K tiles of the 3-term split for a 64-wide factor (K = 64 = 8 tf32 K-steps, two 128-byte swizzle atoms along
+// K), K-concatenated into a single N = 64 accumulator: 24 MMAs + the commits under one elect.sync.
+//   B tile layout: [hi: atom 0 | atom 1][lo: atom 0 | atom 1], each atom = 64 rows x 128 B (ATOM = 512 descriptor units)
+__device__ __forceinline__ void umma_tile_cat64(uint32_t d_tmem, uint32_t a_hi, uint64_t bdesc, uint32_t idesc_n, uint32_t bar_t,
+                                                uint32_t bar_b, uint32_t bar_acc, uint32_t chunk_end) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q, p0, p1, pc;\n\t"
+      ".reg .b32 ah0, ah1, ah2, ah3, ah4, ah5, ah6, ah7, al0, al1, al2, al3, al4, al5, al6, al7;\n\t"
+      ".reg .b64 bh0, bh1, bh2, bh3, bh4, bh5, bh6, bh7, bl0, bl1, bl2, bl3, bl4, bl5, bl6, bl7;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p0, 0, 0;\n\t"
+      "setp.eq.b32 p1, 0, 0;\n\t"
+      "setp.ne.b32 pc, %7, 0;\n\t"
+      "and.pred pc, pc, q;\n\t"
+      "add.u32 ah0, %1, 0;\n\t"
+      "add.u32 al0, %1, 64;\n\t"
+      "add.u64 bh0, %2, 0;\n\t"
+      "add.u64 bl0, %2, 1024;\n\t"
+      "add.u32 ah1, %1, 8;\n\t"
+      "add.u32 al1, %1, 72;\n\t"
+      "add.u64 bh1, %2, 2;\n\t"
+      "add.u64 bl1, %2, 1026;\n\t"
+      "add.u32 ah2, %1, 16;\n\t"
+      "add.u32 al2, %1, 80;\n\t"
+      "add.u64 bh2, %2, 4;\n\t"
+      "add.u64 bl2, %2, 1028;\n\t"
+      "add.u32 ah3, %1, 24;\n\t"
+      "add.u32 al3, %1, 88;\n\t"
+      "add.u64 bh3, %2, 6;\n\t"
+      "add.u64 bl3, %2, 1030;\n\t"
+      "add.u32 ah4, %1, 32;\n\t"
+      "add.u32 al4, %1, 96;\n\t"
+      "add.u64 bh4, %2, 512;\n\t"
+      "add.u64 bl4, %2, 1536;\n\t"
+      "add.u32 ah5, %1, 40;\n\t"
+      "add.u32 al5, %1, 104;\n\t"
+      "add.u64 bh5, %2, 514;\n\t"
+      "add.u64 bl5, %2, 1538;\n\t"
+      "add.u32 ah6, %1, 48;\n\t"
+      "add.u32 al6, %1, 112;\n\t"
+      "add.u64 bh6, %2, 516;\n\t"
+      "add.u64 bl6, %2, 1540;\n\t"
+      "add.u32 ah7, %1, 56;\n\t"
+      "add.u32 al7, %1, 120;\n\t"
+      "add.u64 bh7, %2, 518;\n\t"
+      "add.u64 bl7, %2, 1542;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah0], bh0, %3, p0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah4], bh4, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah5], bh5, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah6], bh6, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah7], bh7, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah0], bl0, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bl1, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bl2, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bl3, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah4], bl4, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah5], bl5, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah6], bl6, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah7], bl7, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al0], bh0, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al1], bh1, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al2], bh2, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al3], bh3, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al4], bh4, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al5], bh5, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al6], bh6, %3, p1;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al7], bh7, %3, p1;\n\t"
+      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t"
+      "@q  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "}\n"
+      ::"r"(d_tmem), "r"(a_hi), "l"(bdesc), "r"(idesc_n), "r"(bar_t), "r"(bar_b), "r"(bar_acc), "r"(chunk_end)
+      : "memory");
+}
+
 // the commits of a tile without its MMAs (timing ablations only)
 __device__ __forceinline__ void umma_commits_only(uint32_t bar_t, uint32_t bar_b, uint32_t bar_acc, uint32_t chunk_end) {
   asm volatile(
@@ -435,9 +514,15 @@ void tc_launch_split_wt(const float* W, int64_t ldw, float* Bcat, int64_t ldb, i
 // fused KL contractions (dnmf_tc_kl.cu)
 int64_t tc_kl_workspace_bytes(int op, int64_t m, int64_t n, int64_t k);
 bool tc_kl_supported(int64_t k);
+// the 64-wide build (dnmf_tc_kl64.cu): 32 < k <= 64
+int64_t tc_kl_workspace_bytes_k64(int op, int64_t m, int64_t n, int64_t k);
+bool tc_kl_supported_k64(int64_t k);
 struct TcPartials;
 int tc_kl_run(int mode, const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* out,
               int64_t ldo, int64_t m, int64_t n, int k, float eps, int transposed_out, void* ws, int64_t ws_bytes,
               cudaStream_t st, TcPartials* defer = nullptr);
+int tc_kl_run_k64(int mode, const float* A, int64_t lda, const float* W, int64_t ldw, const float* H, int64_t ldh, float* out,
+                  int64_t ldo, int64_t m, int64_t n, int k, float eps, int transposed_out, void* ws, int64_t ws_bytes,
+                  cudaStream_t st, TcPartials* defer = nullptr);
 
 }  // namespace dnmf

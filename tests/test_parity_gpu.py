@@ -131,7 +131,7 @@ def test_multi_rank_matches_reference(case):
 
 
 @pytest.mark.parametrize('name', ['u2048k32_1x1_fro_mu_i100', 'u2048k32_1x1_kl_mu_i100', 'u2048k64_1x1_fro_mu_i10',
-                                  'u2048k10_1x1_kl_mu_i10'])
+                                  'u2048k10_1x1_kl_mu_i10', 'u2048k64_1x1_kl_mu_i10'])
 def test_generic_and_tensor_core_paths_agree_with_reference(name):
     """Both device code paths (tcgen05 and generic CUDA-core) are held to the same reference tolerance on shards
     large enough for the tcgen05 kernels; fit_worker asserts which kernels each arm actually ran."""

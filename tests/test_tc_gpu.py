@@ -115,12 +115,15 @@ def test_deterministic(ops):
 KL_SHAPES = [(128, 32, 32), (256, 96, 32), (1000, 1000, 32), (515, 2052, 32), (2048, 2048, 32), (4100, 300, 32),
              (1024, 8192, 32), (8192, 1024, 32),
              # k < 32 rides along zero-padded
-             (1000, 1000, 4), (2048, 2048, 10), (515, 2052, 20), (4100, 300, 1), (1024, 8192, 31)]
+             (1000, 1000, 4), (2048, 2048, 10), (515, 2052, 20), (4100, 300, 1), (1024, 8192, 31),
+             # 32 < k <= 64: the 64-wide build of the kernel (dnmf_tc_kl64.cu)
+             (128, 64, 64), (256, 96, 64), (1000, 1000, 64), (515, 2052, 48), (2048, 2048, 64), (4100, 300, 33),
+             (1024, 8192, 64), (8192, 1024, 40)]
 
 
 @pytest.mark.parametrize('m,n,k', KL_SHAPES)
 def test_kl_tensor_path(ops, m, n, k):
-    """Fused KL contractions on the tcgen05 path (k <= 32; the kernel is written for 32 factor columns): S = W H recomputed on the tensor cores, U = A / (S + eps)
+    """Fused KL contractions on the tcgen05 path (k <= 64; kernels built for 32 and 64 factor columns): S = W H recomputed on the tensor cores, U = A / (S + eps)
     in the splitter warps, second MMA; compared with float64 numpy and with the generic fused kernels."""
     from pydnmfk_b200 import _lib as L
     rs = np.random.RandomState(3)
@@ -215,18 +218,15 @@ def test_fused_epilogue_is_bit_identical(ops, m, n, k):
     assert torch.equal(H1, H2)
     H3 = H.clone(); ops.mu_update_h(H3, ops.wta(A, W), G_w, eps)          # and the non-transposed plain form
     assert torch.equal(H1, H3)
-    if k <= 32:
-        x2, x1 = ops.rowsum(H), ops.colsum(W)
-        W1 = W.clone(); ops.kl_update_w(W1, ops.kl_uht(A, W, H, eps), x2, eps)
-        view = ops.kl_uht_p(A, W, H, eps); assert view is not None
-        W2 = W.clone(); ops.kl_update_w_p(W2, view, x2, eps)
-        assert torch.equal(W1, W2)
-        H1 = H.clone(); ops.kl_update_h(H1, ops.kl_wtu(A, W, H, eps, transposed_out=True), x1, eps, y_transposed=True)
-        view = ops.kl_wtu_p(A, W, H, eps); assert view is not None
-        H2 = H.clone(); ops.kl_update_h_p(H2, view, x1, eps)
-        assert torch.equal(H1, H2)
-    else:
-        assert ops.kl_uht_p(A, W, H, eps) is None         # not on the tcgen05 path: the caller falls back
+    x2, x1 = ops.rowsum(H), ops.colsum(W)
+    W1 = W.clone(); ops.kl_update_w(W1, ops.kl_uht(A, W, H, eps), x2, eps)
+    view = ops.kl_uht_p(A, W, H, eps); assert view is not None
+    W2 = W.clone(); ops.kl_update_w_p(W2, view, x2, eps)
+    assert torch.equal(W1, W2)
+    H1 = H.clone(); ops.kl_update_h(H1, ops.kl_wtu(A, W, H, eps, transposed_out=True), x1, eps, y_transposed=True)
+    view = ops.kl_wtu_p(A, W, H, eps); assert view is not None
+    H2 = H.clone(); ops.kl_update_h_p(H2, view, x1, eps)
+    assert torch.equal(H1, H2)
 
 
 def test_fused_epilogue_falls_back(ops):

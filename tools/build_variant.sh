@@ -10,7 +10,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 bash "${HERE}/build.sh" > /dev/null
 mkdir -p "${HERE}/build_${NAME}"
 pids=()
-for f in dnmf_tc dnmf_tc_kl; do
+for f in dnmf_tc dnmf_tc_kl dnmf_tc_kl64; do
   "${NVCC}" "${FLAGS[@]}" ${DEFS} -c -o "${HERE}/build_${NAME}/${f}.o" "${HERE}/${f}.cu" &
   pids+=($!)
 done
