@@ -265,6 +265,13 @@ int64_t dnmf_matvec_workspace_bytes(int64_t rows, int64_t cols, int trans);
 int dnmf_matvec_f64(const void* A, int64_t lda, int64_t rows, int64_t cols, const double* x, double* y, int trans,
                     int dtype, void* ws, int64_t ws_bytes, void* stream);
 int dnmf_power_normalize(const double* y, const double* v_last, double* v_out, double* r, int64_t d, void* stream);
+/* the whole loop `while True: v = normalize(B @ v); if |<v, v_prev>| > thr: break` (dist_svd.py:117-134) in ONE launch
+ * for a small Gram matrix B [d x d], d <= 512 (same arithmetic as dnmf_matvec_f64 + dnmf_power_normalize per step);
+ * thr = 1 - eps as the reference computes it; cmp_f32 = 1 when that value is a float32 scalar (fp32 data): numpy then
+ * compares in float32, which stops later than the float64 comparison would;
+ * v: start vector in, result out; scratch: 2 d doubles; iters_out (device int, may be NULL): steps taken */
+int dnmf_power_iterate(const void* B, int64_t ldb, int64_t d, double* v, double thr, int cmp_f32, int max_iter,
+                       double* scratch, int* iters_out, int dtype, void* stream);
 int dnmf_div_store(const double* src, const double* sq, double* dst, int64_t n, int64_t stride, void* stream);
 int dnmf_posneg_colsumsq(const double* X, int64_t ldx, int64_t rows, int64_t k, double* out, void* stream);
 int dnmf_nnsvd_pick(const double* X, int64_t ldx, int64_t rows, int64_t k, const double* coef, const int32_t* pos,

@@ -88,6 +88,7 @@ SIGNATURES = {
     'dnmf_matvec_workspace_bytes': (i64, [i64, i64, i32]),
     'dnmf_matvec_f64': (i32, [vp, i64, i64, i64, vp, vp, i32, i32, vp, i64, vp]),
     'dnmf_power_normalize': (i32, [vp, vp, vp, vp, i64, vp]),
+    'dnmf_power_iterate': (i32, [vp, i64, i64, vp, dbl, i32, i32, vp, vp, i32, vp]),
     'dnmf_div_store': (i32, [vp, vp, vp, i64, i64, vp]),
     'dnmf_posneg_colsumsq': (i32, [vp, i64, i64, i64, vp, vp]),
     'dnmf_nnsvd_pick': (i32, [vp, i64, i64, i64, vp, vp, vp, i64, i32, vp]),

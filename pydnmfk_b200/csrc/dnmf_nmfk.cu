@@ -236,6 +236,53 @@ power_normalize_kernel(const double* __restrict__ y, const double* __restrict__ 
   if (threadIdx.x == 0) r[0] = t;
 }
 
+// The whole power iteration of dist_svd.py:117-134 on ONE CTA for small Gram matrices (d <= 512): per step y = B v
+// (warp per row, the summation order of matvec_rows_kernel), v' = y / ||y||, r = <v', v> (the order of
+// power_normalize_kernel), until |r| > thr -- the same arithmetic as the launch-per-step loop, without its host round trip
+// per step.  cur / nxt: 2 d doubles of scratch; v holds the start vector on entry and the result on exit.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+power_iterate_kernel(const T* __restrict__ B, int64_t ldb, int64_t d, double* __restrict__ v, double* __restrict__ scratch,
+                     double thr, int cmp_f32, int max_iter, int* __restrict__ iters_out) {
+  __shared__ double red[32];
+  __shared__ double nrm, rdot;
+  double* y = scratch;
+  double* nxt = scratch + d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int it = 0;
+  for (; it < max_iter;) {
+    for (int64_t row = warp; row < d; row += 32) {
+      double s = 0.0;
+      for (int64_t j = lane; j < d; j += 32) s += (double)B[row * ldb + j] * v[j];
+      s = warp_sum(s);
+      if (lane == 0) y[row] = s;
+    }
+    __syncthreads();
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) s += y[i] * y[i];
+    s = block_sum<1024>(s, red);
+    if (threadIdx.x == 0) nrm = sqrt(s);
+    __syncthreads();
+    double t = 0.0;
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) {
+      const double x = y[i] / nrm;
+      nxt[i] = x;
+      t += x * v[i];
+    }
+    t = block_sum<1024>(t, red);
+    if (threadIdx.x == 0) rdot = t;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) v[i] = nxt[i];
+    ++it;
+    // |r| > thr, compared in float32 when the caller's threshold is a float32 scalar (numpy compares a Python float with
+    // np.float32(1 - eps) in float32: the reference's stopping rule for fp32 data, dist_svd.py:126)
+    const bool done = cmp_f32 ? ((float)fabs(rdot) > (float)thr) : (fabs(rdot) > thr);
+    __syncthreads();
+    if (done) break;
+  }
+  if (threadIdx.x == 0 && iters_out != nullptr) *iters_out = it;
+}
+
 // dst[i*stride] = src[i] / sqrt(sq[0])       (u = u_unnorm / sig, stored as a column; dist_svd.py:167-176)
 __global__ void __launch_bounds__(256)
 div_store_kernel(const double* __restrict__ src, const double* __restrict__ sq, double* __restrict__ dst, int64_t n,
@@ -389,6 +436,16 @@ int dnmf_power_normalize(const double* y, const double* v_last, double* v_out, d
   DNMF_CHECK_ARG(d >= 1 && y && v_last && v_out && r, "shape / null pointer");
   power_normalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(y, v_last, v_out, r, d);
   DNMF_LAUNCH_CHECK("power_normalize_kernel");
+  return 0;
+}
+
+int dnmf_power_iterate(const void* B, int64_t ldb, int64_t d, double* v, double thr, int cmp_f32, int max_iter,
+                       double* scratch, int* iters_out, int dtype, void* stream) {
+  if (int rc = check_dtype(dtype)) return rc;
+  DNMF_CHECK_ARG(d >= 1 && d <= 512 && ldb >= d && B && v && scratch && max_iter >= 1, "shape / null pointer (d <= 512)");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, (power_iterate_kernel<T><<<1, 1024, 0, st>>>((const T*)B, ldb, d, v, scratch, thr, cmp_f32, max_iter, iters_out)));
+  DNMF_LAUNCH_CHECK("power_iterate_kernel");
   return 0;
 }
 

@@ -553,6 +553,19 @@ class DeviceOps:
                self._stream())
         return v
 
+    def power_iterate(self, B, v0, thr, max_iter=1000000):
+        """The whole power iteration on B [d x d] (d <= 512) in one launch, until |<v, v_prev>| > thr; returns the unit
+        vector.  ``thr`` is the caller's ``1. - eps`` scalar: when it is a numpy float32 the comparison runs in float32, as
+        numpy's own ``python_float > np.float32`` does (the reference's stopping rule for fp32 data)."""
+        d = B.shape[0]
+        assert B.shape == (d, d) and v0.dtype == torch.float64 and v0.numel() == d
+        v = v0.clone()
+        scratch = self.empty((2 * d,), torch.float64)
+        cmp32 = 1 if isinstance(thr, np.float32) else 0
+        L.call('dnmf_power_iterate', B.data_ptr(), _ld(B), d, v.data_ptr(), float(thr), cmp32, int(max_iter),
+               scratch.data_ptr(), None, _DT[B.dtype], self._stream())
+        return v
+
     def div_store(self, src, sq, dst_col):
         """dst_col (a strided column view) = src / sqrt(sq)."""
         L.call('dnmf_div_store', src.data_ptr(), sq.data_ptr(), dst_col.data_ptr(), src.numel(),

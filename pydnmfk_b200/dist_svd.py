@@ -16,6 +16,8 @@ from datetime import datetime
 from math import sqrt
 from random import normalvariate
 
+import os
+
 import numpy as np
 import torch
 
@@ -94,6 +96,10 @@ class DistSVD():
             B = self.grid_comm.allreduce_(self.ops.gram_wide(self.mat_for_1D))                 # mat^T mat   (n x n)
         else:
             B = self.grid_comm.allreduce_(self.ops.outer_gram_wide(self.mat_for_1D, self.A))   # mat A^T     (m x m)
+        if d <= 512 and B.dtype in (torch.float32, torch.float64) and os.environ.get('DNMF_POWER_ITERATE', '1') != '0':
+            # small Gram matrix: the whole loop in one launch (same arithmetic, no host round trip per step)
+            self.currV = self.ops.power_iterate(B, cur, 1. - self.eps)
+            return
         r = self.ops.empty((1,), torch.float64)
         while True:
             cur = self.ops.power_normalize(self.ops.matvec_f64(B, cur), cur, r)

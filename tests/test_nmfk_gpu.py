@@ -264,3 +264,30 @@ def test_nmfk_ensemble_over_replica_groups_matches_reference(gold, name, world):
         assert np.allclose(o['k%d/clusterSilhouetteCoefficients' % k], g('clusterSilhouetteCoefficients'), rtol=0, atol=1e-3)
         assert np.allclose(o['k%d/ErrTol' % k], g('ErrTol'), rtol=1e-4)
         assert np.allclose(o['k%d/L_err' % k], g('L_err'), rtol=2e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize('d', [1, 5, 21, 96, 300, 512])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64], ids=['f32', 'f64'])
+def test_power_iterate_equals_the_stepwise_loop(d, dtype):
+    """dnmf_power_iterate (the whole loop of dist_svd.py:117-134 in one launch) must return exactly the vector of the
+    launch-per-step loop (dnmf_matvec_f64 + dnmf_power_normalize until |<v, v_prev>| > 1 - eps)."""
+    from pydnmfk_b200 import device as D
+    ops = D.default_ops()
+    rs = np.random.RandomState(d)
+    X = rs.rand(3 * d + 2, d)
+    B = (X.T @ X).astype(dtype)                        # a Gram matrix, like svd1D's
+    v0 = rs.randn(d)
+    v0 /= np.linalg.norm(v0)
+    Bd = _dev(B)
+    for eps in (float(np.finfo(np.float32).eps), np.finfo(np.float32).eps, np.finfo(np.float64).eps * 1e4):
+        thr = 1. - eps                                   # np.float32 for the float32 eps: numpy then compares in float32
+        cur = _dev(v0)
+        r = torch.zeros(1, dtype=torch.float64, device='cuda')
+        steps = 0
+        while True:
+            cur = ops.power_normalize(ops.matvec_f64(Bd, cur), cur, r)
+            steps += 1
+            if abs(float(r.item())) > thr or steps > 100000:
+                break
+        got = ops.power_iterate(Bd, _dev(v0), thr)
+        assert torch.equal(got, cur), (type(thr), steps, float((got - cur).abs().max()))
