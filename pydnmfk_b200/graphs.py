@@ -26,6 +26,17 @@ def graphs_enabled(comm, method):
     return True
 
 
+_side_streams = {}
+
+
+def _capture_stream(device):
+    """One capture stream per device (capture must not run on the legacy default stream)."""
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 class StepGraphs:
     """`plain()` / `clamped()` replay the captured step (+ clamp).  Capture happens lazily on first use; the callables
     must already have been run eagerly once (kernel attributes set, tf32 calibration done, workspace sized)."""
@@ -36,13 +47,25 @@ class StepGraphs:
         self._pool = None
 
     def _capture(self, with_clamp):
+        # Manual capture on a side stream.  `with torch.cuda.graph(g)` would also run gc.collect() and
+        # torch.cuda.empty_cache() on entry: ~20 ms per capture, as much as a whole 1000-iteration fit of an NMFk
+        # ensemble member costs on the device (two captures per fit; tools/prof_cfg5.py).
         g = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize()
-        kw = {'pool': self._pool} if self._pool is not None else {}
-        with torch.cuda.graph(g, **kw):
-            self._step()
-            if with_clamp:
-                self._clamp()
+        cur = torch.cuda.current_stream()
+        side = _capture_stream(cur.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            if self._pool is not None:
+                g.capture_begin(pool=self._pool)
+            else:
+                g.capture_begin()
+            try:
+                self._step()
+                if with_clamp:
+                    self._clamp()
+            finally:
+                g.capture_end()
+        cur.wait_stream(side)
         if self._pool is None:
             self._pool = g.pool()
         return g

@@ -37,6 +37,8 @@ def main():
     case = dict(K.CFG5_CASE)
     if '--quick' in sys.argv:                       # script check: a shortened sweep
         case.update(end_k=4, perturbations=4, itr=100)
+    if '--quick1000' in sys.argv:                   # profiling: full-length fits, short sweep
+        case.update(end_k=3, perturbations=4, itr=1000)
     p_r, p_c = case['grid']
     assert world % (p_r * p_c) == 0, 'world must be a multiple of the 2 x 1 factorization grid'
     X = K.wtsi().astype('float32')
@@ -83,7 +85,7 @@ def main():
                 'perturbation_fits': (case['end_k'] - case['start_k'] + 1) * case['perturbations'],
                 'gpu_launches_rank0': int(launches), 'reference_wall_s_2_cpu_ranks_authoring_container': 72.2}
         gpath = os.path.join(K.GOLDEN, 'nmfk_cfg5.npz')
-        if os.path.exists(gpath) and '--quick' not in sys.argv:
+        if os.path.exists(gpath) and '--quick' not in sys.argv and '--quick1000' not in sys.argv:
             g = np.load(gpath)
             pre = 'e2e/%s/0/' % case['name']
             line['reference_nopt'] = int(g[pre + 'nopt'])
@@ -98,6 +100,8 @@ def main():
         print(json.dumps(line), flush=True)
     comm.barrier()
     sys.stdout.flush()
+    if '--quick1000' in sys.argv:
+        return
     os._exit(0)
 
 
