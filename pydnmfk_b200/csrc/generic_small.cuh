@@ -36,15 +36,30 @@ gram_partial_kernel(const T* __restrict__ X, int64_t ldx, int64_t rows, int k, i
       Xs[r][kk] = v;
     }
     __syncthreads();
-#pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      const int e = t + o * NT;
-      if (e < KP * KP) {
-        const int i = e / KP, j = e % KP;
-        T a = acc[o];
+    if (NT % KP == 0) {
+      // every output of this thread has the same column j = t % KP (KP divides the block size): load Xs[r][j] once
+      // per r and reuse it for the thread's NO outputs (same summation order per output: r ascending)
+      const int j = t % KP, i0 = t / KP;
 #pragma unroll 8
-        for (int r = 0; r < TR; ++r) a = fma(Xs[r][i], Xs[r][j], a);
-        acc[o] = a;
+      for (int r = 0; r < TR; ++r) {
+        const T xj = Xs[r][j];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          const int i = i0 + o * (NT / KP);
+          if (i < KP) acc[o] = fma(Xs[r][i], xj, acc[o]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        const int e = t + o * NT;
+        if (e < KP * KP) {
+          const int i = e / KP, j = e % KP;
+          T a = acc[o];
+#pragma unroll 8
+          for (int r = 0; r < TR; ++r) a = fma(Xs[r][i], Xs[r][j], a);
+          acc[o] = a;
+        }
       }
     }
   }
@@ -153,6 +168,22 @@ col_update_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ X, int64
     Gs[idx] = (l < k && j < k) ? G[l * k + j] : T(0);
   }
   __syncthreads();
+  // Y given column-major per column (ysk == 1: the [x][ldp] layout of the split-K partials): a thread would read its
+  // column as KP consecutive elements, 128 bytes apart from its neighbour's -- stage the block's columns through shared
+  // memory with coalesced loads instead (and add the splits there).
+  constexpr bool kStage = sizeof(T) * ((KP + 1) * kColUpdThreads + KP * KP) <= 46 * 1024;    // next to Gs in 48 KB
+  __shared__ T Ys[kStage ? kColUpdThreads * (KP + 1) : 1];
+  const bool staged = kStage && ysk == 1;
+  if (staged) {
+    const int64_t c0 = (int64_t)blockIdx.x * kColUpdThreads;
+    for (int e = t; e < kColUpdThreads * KP; e += kColUpdThreads) {
+      const int col = e / KP, kk = e % KP;
+      T v = T(0);
+      if (c0 + col < n && kk < k) v = sum_splits(Y + (c0 + col) * ysc + kk, splits, sstride);
+      Ys[col * (KP + 1) + kk] = v;
+    }
+    __syncthreads();
+  }
   const int64_t c = (int64_t)blockIdx.x * kColUpdThreads + t;
   if (c >= n) return;
   T h[KP];
@@ -165,7 +196,7 @@ col_update_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ X, int64
         T d = T(0);
 #pragma unroll
         for (int l = 0; l < KP; ++l) d = fma(Gs[kk * KP + l], h[l], d);
-        T v = h[kk] + sum_splits(Y + (int64_t)kk * ysk + c * ysc, splits, sstride) - d;
+        T v = h[kk] + (staged ? Ys[t * (KP + 1) + kk] : sum_splits(Y + (int64_t)kk * ysk + c * ysc, splits, sstride)) - d;
         h[kk] = v > p0 ? v : p0;
       }
     }
@@ -178,7 +209,7 @@ col_update_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ X, int64
       if (kk < k) {
         T d = T(0);
         T res;
-        const T y = sum_splits(Y + (int64_t)kk * ysk + c * ysc, splits, sstride);
+        const T y = staged ? Ys[t * (KP + 1) + kk] : sum_splits(Y + (int64_t)kk * ysk + c * ysc, splits, sstride);
         if (MODE == 0) {
 #pragma unroll
           for (int l = 0; l < KP; ++l) d = fma(h[l], Gs[l * KP + kk], d);
