@@ -367,8 +367,8 @@ int dnmf_kl_update_h_p(void* H, int64_t ldh, const int64_t* view4, const void* x
   DNMF_VIEW(view4);
   if (n == 0 || k == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  kl_update_h_kernel<float><<<(unsigned)ceil_div(k * n, 256), 256, 0, st>>>((float*)H, ldh, vp_, 1, vld_, (const float*)x, (int)k, n, (float)eps, clamp, vsp_, vss_);
-  DNMF_LAUNCH_CHECK("kl_update_h_kernel<p>");
+  kl_update_h_staged_kernel<float><<<(unsigned)ceil_div(n, 64), 256, 0, st>>>((float*)H, ldh, vp_, vld_, (const float*)x, (int)k, n, (float)eps, clamp, vsp_, vss_);
+  DNMF_LAUNCH_CHECK("kl_update_h_staged_kernel");
   return 0;
 }
 #undef DNMF_VIEW

@@ -252,6 +252,31 @@ __global__ void kl_update_h_kernel(T* __restrict__ H, int64_t ldh, const T* __re
   H[(int64_t)kk * ldh + c] = v;
 }
 
+// The same update with Y given as split-K partials in the [column][ldp] layout: a block stages 64 columns through shared
+// memory (coalesced loads along the factor index, splits added in order) and then updates H with the column index fastest.
+template <typename T>
+__global__ void __launch_bounds__(256)
+kl_update_h_staged_kernel(T* __restrict__ H, int64_t ldh, const T* __restrict__ Yp, int64_t ldp, const T* __restrict__ x,
+                          int k, int64_t n, T eps, int clamp, int splits, int64_t sstride) {
+  constexpr int CB = 64;
+  __shared__ T Ys[CB][DNMF_MAX_K + 1];
+  const int64_t c0 = (int64_t)blockIdx.x * CB;
+  for (int e = threadIdx.x; e < CB * k; e += 256) {
+    const int col = e / k, kk = e % k;
+    Ys[col][kk] = (c0 + col < n) ? sum_splits(Yp + (c0 + col) * ldp + kk, splits, sstride) : T(0);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < CB * k; e += 256) {
+    const int kk = e / CB, col = e % CB;
+    const int64_t c = c0 + col;
+    if (c < n) {
+      T v = H[(int64_t)kk * ldh + c] * (Ys[col][kk] / (x[kk] + eps));
+      if (clamp) v = v > eps ? v : eps;
+      H[(int64_t)kk * ldh + c] = v;
+    }
+  }
+}
+
 template <typename T>
 __global__ void clamp_min_kernel(T* __restrict__ X, int64_t ldx, int64_t rows, int64_t cols, T lo) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
