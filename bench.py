@@ -188,6 +188,8 @@ def cpu_baseline(args, steps, warmup, full=False):
     are scaled by the element ratio (the loop is O(m n k)) -- `sample` says which."""
     import multiprocessing as mp
     m, n = _cpu_sample_side(args, full)
+    if getattr(args, 'ref_rows', None):
+        m = min(m, int(args.ref_rows))          # a row slab of the full-width matrix (time budget of the reference arm)
     k = args.k
     cores = os.cpu_count() or 1
     shard = max(1, m // cores)
@@ -228,12 +230,37 @@ def workload_config(args, world=None):
                         'one row shard per GPU' % (args.m, args.n, args.k), 'norms': args.norms}
 
 
+def _bounded_rows_for_budget(args, steps, warmup, budget_s):
+    """Rows of the matrix the reference arm can afford within `budget_s` seconds for `steps + warmup` iterations per norm:
+    a one-iteration calibration on a thin slab (512 rows per rank, full width) gives the host's seconds per element, the
+    loop is O(m n k).  Returns None when the full workload fits the budget."""
+    cores = os.cpu_count() or 1
+    m_full, _ = _cpu_sample_side(args, True)
+    m_cal = min(m_full, cores * 512)
+    probe = argparse.Namespace(**vars(args))
+    probe.m, probe.cpu_sample = m_cal, m_cal
+    cal = cpu_baseline(probe, steps=1, warmup=1, full=True)
+    # cal['measured_s'] = one timed iteration per norm on m_cal rows
+    predicted = cal['measured_s'] * (float(m_full) / m_cal) * (steps + warmup)
+    if predicted <= budget_s:
+        return None
+    rows = int(m_full * budget_s / predicted) // cores * cores
+    return max(rows, cores * 256)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    cb = cpu_baseline(args, max(1, args.steps), max(0, args.warmup), full=True)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # the whole run must end within a few minutes whatever --steps / --warmup ask for: full workload when the host
+    # affords it (16 cores: ~10 s per FRO + KL iteration pair at 65536^2), else a bounded row slab of it, scaled
+    rows = _bounded_rows_for_budget(args, steps, warmup, float(os.environ.get('DNMF_REF_BUDGET_S', '200')))
+    if rows is not None:
+        args = argparse.Namespace(**vars(args))
+        args.ref_rows = rows
+    cb = cpu_baseline(args, steps, warmup, full=True)
     wall = time.perf_counter() - t0
     steps_total = args.steps * len(args.norms.split(','))
     line = {
