@@ -43,6 +43,10 @@ def draw_global(case, rs):
         A[rs.rand(m, n) < 0.6] = 0
         A[rs.permutation(m)[:2], :] = 0
         A[:, rs.permutation(n)[:2]] = 0
+    elif kind == 'swim':           # the reference's data/swim.mat (1024 x 256 uint8 images), stored as a test fixture
+        import os
+        A = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'swim_X.npy'))
+        assert A.shape == (m, n)
     else:
         raise ValueError(kind)
     A = A.astype(case['dtype'])
@@ -127,6 +131,11 @@ def _grid_cases():
     c = _case('u2048k16_1x1_fro_bcd_i100', 2048, 2048, 16, (1, 1), 'fro', 'bcd', 100, reseed=7)
     c['expect_tc'] = True
     cs.append(c)
+    # BASELINE.json configs[0] itself: data/swim.mat, FRO-MU, k = 4, rand init, 1000 iterations on a 4 x 1 grid (the
+    # reference's `mpirun -n 4 python main.py --p_r=4 --p_c=1 --k=4 --fname=swim --init=rand --itr=1000 --norm=fro
+    # --method=mu`, prune off as main.py:28 defaults), plus the same fit on one rank
+    cs.append(_case('swim_4x1_fro_mu_i1000', 1024, 256, 4, (4, 1), 'fro', 'mu', 1000, data='swim', reseed=7))
+    cs.append(_case('swim_1x1_fro_mu_i1000', 1024, 256, 4, (1, 1), 'fro', 'mu', 1000, data='swim', reseed=7))
     # prune path: exact-zero rows/cols, fp32 in -> float64 out (utils.py:195,198)
     for g in ((1, 1), (2, 1), (1, 2), (2, 2)):
         for norm in ('fro', 'kl'):

@@ -83,7 +83,7 @@ SINGLE = [c for c in C.CASES if c['grid'] == (1, 1)]
 MULTI = [c for c in C.CASES if c['grid'] != (1, 1)]
 # a representative multi-rank subset keeps the GPU suite to a few minutes (process spawn dominates)
 MULTI_PICK = [c for c in MULTI if c['itr'] in (10, 300) or c['prune'] or c['given_factors'] or c['expect_tc']
-              or (c['method'] == 'bcd' and c['itr'] == 100)]
+              or (c['method'] == 'bcd' and c['itr'] == 100) or c['data'] == 'swim']
 MULTI_PICK = [c for c in MULTI_PICK if not (c['name'].startswith('u64x48k4') and c['dtype'] == 'float64' and c['grid'] in ((1, 2), (4, 2)))]
 
 
