@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument('--m', type=int, default=None)
     ap.add_argument('--n', type=int, default=None)
     ap.add_argument('--k', type=int, default=None)
+    ap.add_argument('--shard-side', type=int, default=None, help='cfg3: side of the square shard per GPU (default 65536); same as --m, but a name torchrun does not mistake for one of its own options')
     ap.add_argument('--no-verify', action='store_true', help='skip the distributed-vs-one-GPU check of the first step')
     ap.add_argument('--norms', default='fro,kl')
     ap.add_argument('--no-e2e', action='store_true')
@@ -51,6 +52,8 @@ def parse_args():
     ap.add_argument('--force-generic', action='store_true', help='disable the tcgen05 path (A/B runs)')
     ap.add_argument('--no-graph', action='store_true', help='launch every step eagerly instead of replaying a CUDA graph')
     a = ap.parse_args()
+    if a.shard_side is not None:
+        a.m = a.shard_side
     a.m_given, a.n_given, a.k_given = a.m is not None, a.n is not None, a.k is not None
     a.m = a.m if a.m_given else 65536
     a.n = a.n if a.n_given else 65536
@@ -411,7 +414,7 @@ def run_ours(args):
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
+    local = int(os.environ.get('DNMF_BENCH_DEVICE', os.environ.get('LOCAL_RANK', '0')))   # (override: several ranks on one GPU, gloo, script checks)
     cfg = CONFIGS[args.config]
     legs = [l for l in cfg['legs'] if args.config != 'cfg2' or l[0] in args.norms.split(',')]
     # CPU baseline first (forks workers; done before this process creates a CUDA context)
@@ -518,6 +521,28 @@ def run_ours(args):
                     del Wall, W0all
                     torch.cuda.empty_cache()
                 assert rec['replica_max_abs_diff'] <= 1e-6, 'H replicas differ across ranks: %r' % rec
+            if two_d:
+                # 2-D grids (the whole matrix does not fit one GPU at cfg3): the squared error of the updated factors two
+                # independent ways -- (1) the direct residual over the resident shards (all-gathers of W and H + one pass),
+                # (2) the trace identity ||A||^2 - 2 <W, A H^T> + <W^T W, H H^T> through the update's own distributed
+                # contraction (all-gather -> pass -> reduce-scatter) and Grams.  A wrong shard order or collective shows
+                # up as a mismatch; the two share no kernel on the A side.
+                try:
+                    res = alg._residual_global(W, H)                 # [||A - W H||^2, ||A||^2], all-reduced
+                    AH = alg._AH(H)                                  # rows of this rank's W shard
+                    tt = ops.trace_terms(W, AH, alg._gram_W(W), alg._gram_H(H))
+                    tt[:, 1] /= float(world)                         # the Gram term is global on every rank already
+                    tt = comm.allreduce_(tt)
+                    torch.cuda.synchronize()
+                    direct, a2 = float(res[0].item()), float(res[1].item())
+                    trace = a2 - 2.0 * float(tt[0, 0].item()) + float(tt[0, 1].item())
+                    rec['residual_direct_vs_trace_identity'] = {'direct': direct, 'trace': trace,
+                                                                'rel_diff': abs(direct - trace) / max(direct, 1e-300)}
+                    assert abs(direct - trace) <= 1e-3 * direct, '2-D step: direct residual and trace identity disagree: %r' % rec
+                except AssertionError:
+                    raise
+                except Exception as ex:          # the check must never take the benchmark down
+                    rec['residual_direct_vs_trace_identity'] = {'error': repr(ex)}
             verify['%s-%s' % (norm, method)] = rec
             del alg
             sync_all()
