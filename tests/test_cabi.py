@@ -91,3 +91,18 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                     '-L', libdir, '-l:libdnmf.so', '-Wl,-rpath,' + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert 'sm_100a' in out and 'bad argument' in out
+
+
+def test_ctypes_signatures_match_the_header_arity():
+    """Every entry point's ctypes argument list has exactly as many entries as the C declaration has parameters (a
+    signature that drifts from the header corrupts the call silently: ctypes does not know the C prototype)."""
+    from pydnmfk_b200 import _lib as L
+    src = open(os.path.join(ROOT, 'include', 'dnmf.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    decls = re.findall(r'\b(dnmf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S)
+    assert len(decls) >= 60
+    for name, params in decls:
+        params = ' '.join(params.split())
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        res, args = L.SIGNATURES[name]
+        assert len(args) == n, '%s: header has %d parameters, _lib.py binds %d' % (name, n, len(args))
