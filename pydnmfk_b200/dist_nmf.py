@@ -427,15 +427,32 @@ class nmf_algorithms_1D(_AlgBase):
 
     @comm_timing()
     def global_mm(self, A, B, p=-1):
-        """Only the two A-streaming products of the update loop are supported:
-        ``global_mm(A_ij, H_j.T, p_c)`` and ``global_mm(W_i.T, A_ij, p_r)`` (dist_nmf.py:687-711)."""
+        """``A @ B`` all-reduced iff ``p != 1`` (dist_nmf.py:687-711).  The two A-streaming products of the update loop,
+        ``global_mm(A_ij, H_j.T, p_c)`` and ``global_mm(W_i.T, A_ij, p_r)``, run as one pass over the resident shard; any
+        other pair of matrices goes through the same skinny contraction in column chunks of the factor width the kernels
+        support (the left operand is streamed once per chunk)."""
+        dt = self.A_ij.dtype
         if A is self.A_ij or A is self._A_orig:
-            out = self.ops.ah(self.A_ij, D.to_device_view(B, self.A_ij.dtype).t().contiguous())
-        elif B is self.A_ij or B is self._A_orig:
-            out = self.ops.wta(self.A_ij, D.to_device_view(A, self.A_ij.dtype).t().contiguous())
+            Bt = D.to_device_view(B, dt).t().contiguous()
+            if Bt.shape[0] <= D.L.MAX_K:
+                out = self.ops.ah(self.A_ij, Bt)
+            else:
+                out = self._mm_chunked(self.A_ij, D.to_device_view(B, dt))
+        elif (B is self.A_ij or B is self._A_orig) and D.to_device_view(A, dt).shape[0] <= D.L.MAX_K:
+            out = self.ops.wta(self.A_ij, D.to_device_view(A, dt).t().contiguous())
         else:
-            raise NotImplementedError('global_mm: one operand must be the resident shard A_ij')
+            out = self._mm_chunked(D.to_device_view(A, dt).contiguous(), D.to_device_view(B, dt))
         return self.comm1.allreduce_(out) if p != 1 else out
+
+    def _mm_chunked(self, A, B):
+        """A [r x c] @ B [c x s] for any s: out[:, j0:j1] = A (B[:, j0:j1]^T)^T in chunks of <= MAX_K columns."""
+        r, s_cols = A.shape[0], B.shape[1]
+        out = self.ops.empty((r, s_cols), A.dtype)
+        step = D.L.MAX_K
+        for j0 in range(0, s_cols, step):
+            j1 = min(s_cols, j0 + step)
+            out[:, j0:j1] = self.ops.ah(A, B[:, j0:j1].t().contiguous())
+        return out
 
     def _gram_W(self, W):
         G = self.ops.gram(W, trans=False)

@@ -181,6 +181,36 @@ def test_update_objects_accept_numpy_like_the_reference():
         assert str(e.value) == bad[2]
 
 
+def test_public_helpers_accept_any_operands_like_the_reference():
+    """global_mm / global_gram / sum_along_axis of nmf_algorithms_1D (dist_nmf.py:662-711, :775-801) with operands that
+    are NOT the resident shard (the reference's helpers are plain ``A @ B``): chunked skinny contractions."""
+    from pydnmfk_b200.dist_comm import MPI, MPI_comm
+    from pydnmfk_b200.dist_nmf import nmf_algorithms_1D
+    from pydnmfk_b200.utils import parse
+    MPI._reset()
+    comm = MPI.COMM_WORLD
+    MPI_comm(comm, 1, 1)
+    rs = np.random.RandomState(4)
+    A, W, H = rs.rand(60, 45).astype(np.float32), rs.rand(60, 5).astype(np.float32), rs.rand(5, 45).astype(np.float32)
+    p = parse()
+    p.m, p.n, p.p_r, p.p_c, p.k, p.comm1, p.norm, p.method = 60, 45, 1, 1, 5, comm, 'fro', 'mu'
+    p.eps, p.W_update, p.itr = np.finfo(np.float32).eps, True, 1
+    alg = nmf_algorithms_1D(A, W, H, params=p)
+    f = np.float64
+
+    def host(t):
+        return t.cpu().numpy() if hasattr(t, 'cpu') else np.asarray(t)
+
+    X, Y = rs.rand(33, 70).astype(np.float32), rs.rand(70, 150).astype(np.float32)      # 150 > 64 output columns: chunked
+    assert T.rel_fro(host(alg.global_mm(X, Y, 1)), X.astype(f) @ Y.astype(f)) < 2e-6
+    assert T.rel_fro(host(alg.global_mm(A, H.T, 1)), A.astype(f) @ H.astype(f).T) < 2e-6          # the update's own calls
+    assert T.rel_fro(host(alg.global_mm(W.T, A, 1)), W.astype(f).T @ A.astype(f)) < 2e-6
+    wide = rs.rand(45, 100).astype(np.float32)                                                   # resident shard x wide matrix
+    assert T.rel_fro(host(alg.global_mm(A, wide, 1)), A.astype(f) @ wide.astype(f)) < 2e-6
+    assert T.rel_fro(host(alg.global_gram(W, 1)), W.astype(f).T @ W.astype(f)) < 2e-6
+    assert T.rel_fro(host(alg.sum_along_axis(H, 1, axis=1)), H.astype(f).sum(1)) < 2e-6
+
+
 def test_ensemble_spread_over_ranks_equals_sequential():
     """NMFk perturbation ensemble (pyDNMFk.py:226-238): spreading the perturbations over ranks gives exactly the
     sequential stacking; the W-fixed regression fit (pyDNMFk.py:245-248) leaves W untouched up to normalisation."""
