@@ -10,7 +10,10 @@ error messages, same helper names (``global_gram``, ``global_mm``, ``AH_glob``, 
 What differs is *where* the arithmetic runs: every numpy expression of the reference is one
 hand-written sm_100a kernel behind ``libdnmf.so`` (see ``device.DeviceOps``), the shard ``A_ij``
 and both factors stay in HBM for the whole fit, the KL path never materialises ``W @ H``,
-and MPI collectives become ``torch.distributed`` (NCCL) collectives on device buffers.  The
+and MPI collectives become NCCL collectives on communicators owned by the library
+(``dist_comm``), or -- for the H half-step of row grids -- one exchange over NVLink peer memory
+(``peer.PeerExchange``).  On the tcgen05 path a MU half-step is two launches: the A-streaming
+pass and an update kernel that sums the pass's split-K partials itself (``DeviceOps.*_p``).  The
 redundant gathers of the reference's 2-D KL/HALS paths are dropped; results are
 unaffected.
 
