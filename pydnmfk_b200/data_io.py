@@ -7,6 +7,7 @@ block ``determine_block_params`` assigns to it and casts to ``precision``.  ``da
 writes the per-rank ``.npy`` factor files of ``data_io.py:175-196``.
 """
 import os
+import struct
 
 import numpy as np
 
@@ -134,8 +135,8 @@ class data_write():
 
     @comm_timing()
     def save_cluster_results(self, params):
-        """Per-k NMFk statistics on rank 0 (data_io.py:199-209): ``results.h5`` with the reference's dataset names when
-        ``h5py`` is importable, else the same names in ``results.npz`` (this image ships no h5py)."""
+        """Per-k NMFk statistics on rank 0 (data_io.py:199-209): ``results.h5`` with the reference's dataset names
+        (``write_results``: h5py when importable, else the minimal earliest-format writer ``h5min`` plus ``results.npz``)."""
         if self.rank == 0:
             write_results(self.fpath, {
                 'clusterSilhouetteCoefficients': params['clusterSilhouetteCoefficients'],
@@ -153,21 +154,34 @@ def _h5py():
 
 
 def write_results(dirpath, datasets):
+    """``results.h5`` with the reference's dataset names (data_io.py:199-209): through ``h5py`` when it is importable, else
+    through the minimal writer of ``h5min`` (earliest-format HDF5; this image ships neither h5py nor libhdf5).  Without
+    h5py the same datasets also go to ``results.npz`` so that a reader never depends on the minimal writer alone."""
     h5 = _h5py()
     if h5 is not None:
         with h5.File(dirpath + 'results.h5', 'w') as hf:
             for name, val in datasets.items():
                 hf.create_dataset(name, data=val)
     else:
+        from . import h5min
+        h5min.write(dirpath + 'results.h5', datasets)
         np.savez(dirpath + 'results.npz', **{k: np.asarray(v) for k, v in datasets.items()})
 
 
 def read_results(dirpath):
     """{dataset name: ndarray} of one k's ``results.h5`` / ``results.npz`` (pyDNMFk.py:278, plot_results.py:117)."""
     h5 = _h5py()
-    if h5 is not None and os.path.exists(os.path.join(dirpath, 'results.h5')):
-        with h5.File(os.path.join(dirpath, 'results.h5'), 'r') as hf:
-            return {k: np.array(hf[k]) for k in hf.keys()}
+    path = os.path.join(dirpath, 'results.h5')
+    if os.path.exists(path):
+        if h5 is not None:
+            with h5.File(path, 'r') as hf:
+                return {k: np.array(hf[k]) for k in hf.keys()}
+        from . import h5min
+        try:
+            return h5min.read(path)
+        except (ValueError, struct.error):       # a file of a newer format version than the minimal reader covers
+            if not os.path.exists(os.path.join(dirpath, 'results.npz')):
+                raise
     with np.load(os.path.join(dirpath, 'results.npz')) as z:
         return {k: z[k] for k in z.files}
 
