@@ -164,8 +164,8 @@ def write_results(dirpath, datasets):
                 hf.create_dataset(name, data=val)
     else:
         from . import h5min
-        h5min.write(dirpath + 'results.h5', datasets)
         np.savez(dirpath + 'results.npz', **{k: np.asarray(v) for k, v in datasets.items()})
+        h5min.write(dirpath + 'results.h5', datasets)
 
 
 def read_results(dirpath):

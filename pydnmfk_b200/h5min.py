@@ -75,6 +75,8 @@ def write(path, datasets):
         a = np.asarray(val)
         if a.dtype.kind == 'f' and a.dtype.itemsize not in (4, 8):
             a = a.astype(np.float64)
+        if a.dtype.kind == 'O':                        # a list of numpy scalars of mixed width and the like
+            a = a.astype(np.float64)
         if a.dtype.kind == 'b':
             a = a.astype(np.int8)
         a = a.astype(a.dtype.newbyteorder('<')).copy(order='C')    # (ascontiguousarray would make a 0-d array 1-d)
