@@ -223,8 +223,14 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int sp = unit / x_blocks;
       const int kt0 = sp * kt_per_split;
       const int kt1 = min(kt_total, kt0 + kt_per_split);
+#if TC_STEP_GROUPS
+      const int tile0 = tile;                      // this group's tiles of the unit, stepping by the group count
+      for (int kt = kt0 + ((group - tile0) & (Cfg::SG - 1)); kt < kt1; kt += Cfg::SG) {
+        tile = tile0 + (kt - kt0);
+#else
       for (int kt = kt0; kt < kt1; ++kt, ++tile) {
         if (Cfg::SG > 1 && (tile & 1) != group) continue;
+#endif
         const int sa = tile % SA, ts = tile % NT;
         const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u;
         mbar_wait(a_full(sa), pa);
@@ -286,6 +292,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(t_full(ts));
         TC_T(t_store);
       }
+#if TC_STEP_GROUPS
+      tile = tile0 + max(0, kt1 - kt0);
+#endif
     }
     if (prof && warp == 2 && lane == 0) {
       prof[blockIdx.x * 16 + 7] = t_afull; prof[blockIdx.x * 16 + 8] = t_load; prof[blockIdx.x * 16 + 9] = t_tfree;

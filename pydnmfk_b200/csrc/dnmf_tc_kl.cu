@@ -438,8 +438,18 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(bar(iXF));
         pxe ^= 1u;
       }
+#if TC_STEP_GROUPS
+      // this group's tiles of the unit, stepping by the group count (the walk over every tile with a modulo test per
+      // tile cost 10 % of the kernel's warp samples, profiles/r02_ncu_source_hotspots.txt)
+      const int tile0 = tile;
+      int first = group - tile0 % KL_GROUPS;
+      if (first < 0) first += KL_GROUPS;
+      for (int kt = kt0 + first; kt < kt1; kt += KL_GROUPS) {
+        tile = tile0 + (kt - kt0);
+#else
       for (int kt = kt0; kt < kt1; ++kt, ++tile) {
         if (tile % KL_GROUPS != group) continue;
+#endif
         const int sa = tile % SA, ts = tile % NT;
         const uint32_t pa = (uint32_t)(tile / SA) & 1u, pt = (uint32_t)(tile / NT) & 1u;
 #if KL_S1 == 2
@@ -613,6 +623,9 @@ tc_kl_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(iTF + ts));
       }
+#if TC_STEP_GROUPS
+      tile = tile0 + max(0, kt1 - kt0);
+#endif
       pair_base += (kt1 - kt0 + 1) >> 1;
     }
     if (MODE == 2 || MODE == 3) {

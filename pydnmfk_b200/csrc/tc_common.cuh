@@ -96,6 +96,11 @@ __device__ __forceinline__ uint32_t xor_all(const uint32_t (&r)[32]) {
 #ifndef TC_EARLY_RELEASE
 #define TC_EARLY_RELEASE 0
 #endif
+// 1: a splitter group steps through its own tiles of a unit; 0 (rounds 1-2 until the last profile): it walks every tile
+// and skips the other groups' -- bit-identical results, 5-13 % slower passes (profiles/r02_ab_step.txt)
+#ifndef TC_STEP_GROUPS
+#define TC_STEP_GROUPS 1
+#endif
 
 // (unit, k-tile) sequence of one persistent CTA, used by the producers' prefetch cursor
 struct TileCursor {
