@@ -22,7 +22,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import nmfk_cases as K  # noqa: E402  (case definition + fixture path only; the checker, not the product)
 from pydnmfk_b200 import _lib as L  # noqa: E402
 from pydnmfk_b200.data_io import read_results  # noqa: E402
 from pydnmfk_b200.dist_comm import MPI, MPI_comm  # noqa: E402
@@ -30,18 +29,24 @@ from pydnmfk_b200.pyDNMFk import PyNMFk  # noqa: E402
 from pydnmfk_b200.utils import parse, determine_block_params  # noqa: E402
 
 
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')          # fixtures only: the example matrix and the reference's statistics
+CFG5_CASE = dict(name='wtsi_2x1_nnsvd_cfg5', grid=(2, 1), init='nnsvd', start_k=2, end_k=10, perturbations=20, itr=1000,
+                 noise_var=0.015, sill_thr=0.9, norm='kl', method='mu')      # = oracle/nmfk_cases.py CFG5_CASE (the golden's name)
+NNSVD_PY_SEED = 4321                                     # `random.seed` before DistSVD draws its start vectors, as in the golden run
+
+
 def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
-    case = dict(K.CFG5_CASE)
+    case = dict(CFG5_CASE)
     if '--quick' in sys.argv:                       # script check: a shortened sweep
         case.update(end_k=4, perturbations=4, itr=100)
     if '--quick1000' in sys.argv:                   # profiling: full-length fits, short sweep
         case.update(end_k=3, perturbations=4, itr=1000)
     p_r, p_c = case['grid']
     assert world % (p_r * p_c) == 0, 'world must be a multiple of the 2 x 1 factorization grid'
-    X = K.wtsi().astype('float32')
+    X = np.load(os.path.join(GOLDEN, 'wtsi_X.npy')).astype('float32')    # data/wtsi.mat['X'] of the reference, 96 x 21
     pos = rank % (p_r * p_c)
     b = determine_block_params(pos, (p_r, p_c), X.shape).determine_block_index_range_asymm()
     A_ij = np.ascontiguousarray(X[b[0][0]:b[1][0] + 1, b[0][1]:b[1][1] + 1])
@@ -62,7 +67,7 @@ def main():
         p.start_k, p.end_k, p.step_k, p.sill_thr = case['start_k'], case['end_k'], 1, case['sill_thr']
         p.perturbations, p.noise_var, p.sampling = case['perturbations'], case['noise_var'], 'uniform'
         p.results_path, p.checkpoint, p.precision = tmp + '/', False, 'float32'
-        random.seed(K.NNSVD_PY_SEED)
+        random.seed(NNSVD_PY_SEED)
         comm.barrier()
         torch.cuda.synchronize()
         L.launch_count(reset=True)
@@ -84,7 +89,7 @@ def main():
                 'n_gpus': world, 'nmfk_wall_s': dt, 'first_run_wall_s': t_warm, 'nopt': nopt, 'expected_nopt_reference_example': 4,
                 'perturbation_fits': (case['end_k'] - case['start_k'] + 1) * case['perturbations'],
                 'gpu_launches_rank0': int(launches), 'reference_wall_s_2_cpu_ranks_authoring_container': 72.2}
-        gpath = os.path.join(K.GOLDEN, 'nmfk_cfg5.npz')
+        gpath = os.path.join(GOLDEN, 'nmfk_cfg5.npz')
         if os.path.exists(gpath) and '--quick' not in sys.argv and '--quick1000' not in sys.argv:
             g = np.load(gpath)
             pre = 'e2e/%s/0/' % case['name']
