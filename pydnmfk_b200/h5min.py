@@ -148,7 +148,7 @@ def write(path, datasets):
 # ---------------------------------------------------------------------------------------------------------------
 # reader (the same subset, parsed from the specification independently of the writer's layout decisions)
 # ---------------------------------------------------------------------------------------------------------------
-def _read_messages(buf, addr):
+def _read_messages(buf, addr, base=0):
     version, _, nmsg, _, size = struct.unpack_from('<BBHII', buf, addr)
     if version != 1:
         raise ValueError('h5min reads version-1 object headers only')
@@ -158,7 +158,7 @@ def _read_messages(buf, addr):
         data = bytes(buf[pos + 8:pos + 8 + msize])
         if mtype == 0x0010:                             # object header continuation: (address, length)
             caddr, clen = struct.unpack_from('<QQ', data, 0)
-            msgs += _read_block(buf, caddr, clen, nmsg - len(msgs) - 1)
+            msgs += _read_block(buf, caddr + base, clen, nmsg - len(msgs) - 1)
         else:
             msgs.append((mtype, data))
         pos += 8 + msize
@@ -185,7 +185,7 @@ def _dtype_of(data):
     raise ValueError('h5min reads fixed-point and floating-point datasets only (class %d)' % cls)
 
 
-def _symbols(buf, btree_addr, heap_data):
+def _symbols(buf, btree_addr, heap_data, base=0):
     """(name, object header address) of every link below a version-1 group B-tree node."""
     sig, ntype, level, used = struct.unpack_from('<4sBBH', buf, btree_addr)
     if sig != b'TREE' or ntype != 0:
@@ -193,9 +193,10 @@ def _symbols(buf, btree_addr, heap_data):
     out, pos = [], btree_addr + 24 + 8                  # skip key[0]
     for _ in range(used):
         child, _key = struct.unpack_from('<QQ', buf, pos)
+        child += base
         pos += 16
         if level > 0:
-            out += _symbols(buf, child, heap_data)
+            out += _symbols(buf, child, heap_data, base)
             continue
         ssig, _ver, _res, nsym = struct.unpack_from('<4sBBH', buf, child)
         if ssig != b'SNOD':
@@ -220,7 +221,7 @@ def read(path):
         raise ValueError('h5min reads version-0 superblocks with 8-byte offsets / lengths only')
     base = struct.unpack_from('<Q', buf, 24)[0] - sb     # addresses are relative to the base address (= the user block size)
     root_header = struct.unpack_from('<Q', buf, 56 + 8)[0] + base
-    stab = [d for t, d in _read_messages(buf, root_header) if t == 0x0011]
+    stab = [d for t, d in _read_messages(buf, root_header, base) if t == 0x0011]
     if not stab:
         raise ValueError('root group is not an old-style (symbol table) group')
     btree_addr, heap_addr = struct.unpack_from('<QQ', stab[0], 0)
@@ -229,8 +230,8 @@ def read(path):
         raise ValueError('bad local heap')
     heap_data = bytes(buf[hdata + base:hdata + base + hsize])
     out = {}
-    for name, oaddr in _symbols(buf, btree_addr + base, heap_data):
-        msgs = dict((t, d) for t, d in _read_messages(buf, oaddr + base) if t in (0x0001, 0x0003, 0x0008))
+    for name, oaddr in _symbols(buf, btree_addr + base, heap_data, base):
+        msgs = dict((t, d) for t, d in _read_messages(buf, oaddr + base, base) if t in (0x0001, 0x0003, 0x0008))
         if len(msgs) < 3:
             continue                                     # a sub-group or something this subset does not cover
         sp = msgs[0x0001]

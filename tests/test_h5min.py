@@ -186,6 +186,22 @@ def test_writer_messages_equal_the_ones_libhdf5_wrote(tmp_path):
     assert np.array_equal(h5min.read(p)['testdouble'], h5min.read(_libhdf5_sample())['testdouble'])
 
 
+def test_reader_handles_a_user_block(tmp_path):
+    """Superblock at 512 behind a user block, base address 512 (what MATLAB does): every address is relative to it."""
+    d = _results(seed=9)
+    p = str(tmp_path / 'plain.h5')
+    h5min.write(p, d)
+    b = bytearray(open(p, 'rb').read())
+    b[24:32] = struct.pack('<Q', 512)                    # base address
+    q = tmp_path / 'userblock.h5'
+    q.write_bytes(b'MATLAB 7.3-like user block'.ljust(512, b' ') + bytes(b))
+    back = h5min.read(str(q))
+    for name, val in d.items():
+        assert np.array_equal(back[name], np.asarray(val)), name
+    with pytest.raises(ValueError):
+        h5min.read(__file__)
+
+
 def test_data_io_results_file(tmp_path, monkeypatch):
     """write_results / read_results: results.h5 exists with or without h5py; the npz twin only without it."""
     d = _results(seed=5)
